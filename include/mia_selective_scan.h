@@ -1,0 +1,125 @@
+/* C ABI of the B200-native selective scan (libmia_scan.so).
+ *
+ * This is the drop-in boundary for the reference's native op
+ *   selective_scan_cuda_oflex.fwd / .bwd
+ *     (R2GenCSR/VMamba/kernels/selective_scan/csrc/selective_scan/cusoflex/selective_scan_oflex.cpp:143-231, 233-355,
+ *      pybind at :357-360),
+ *   selective_scan_cuda_core.fwd / .bwd   (.../cus/selective_scan.cpp:157-164, 241-250)  == oflex with otype == itype,
+ *   and the mamba_ssm signature with the z gate, selective_scan_cuda.fwd / .bwd, as called at
+ *     R2GenCSR/VMamba/classification/models/vmamba.py:255, 266-269 and
+ *     CXPMRG_Bench_MambaXray_VL/arm/Finetuning/mamba_simple.py:693-704 (through mamba_ssm's selective_scan_fn).
+ *
+ * Plain pointers and sizes only: the caller (any host language) owns every buffer, the library
+ * only launches kernels on the stream it is given.  All pointers are DEVICE pointers.  Strides are in
+ * ELEMENTS (like SSMParamsBase, selective_scan_oflex.h:27-60); the innermost (sequence) stride of
+ * u, delta, z, B, C, out, dout, du, ddelta, dz, dB, dC must be 1 (selective_scan_oflex.cpp:167-168,186,188).
+ *
+ * Every entry point returns 0 on success or a negative MIA_E* code; mia_last_error() returns a
+ * thread-local message for the last failure (the Python binding raises RuntimeError with it, mirroring
+ * TORCH_CHECK -> RuntimeError in the reference).  Calls are asynchronous w.r.t. the host and reentrant.
+ */
+#ifndef MIA_SELECTIVE_SCAN_H_
+#define MIA_SELECTIVE_SCAN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIA_ABI_VERSION 1
+
+enum { MIA_F32 = 0, MIA_F16 = 1, MIA_BF16 = 2 };
+
+enum {
+    MIA_OK = 0,
+    MIA_EINVAL = -1,     /* bad shape / dtype / stride / null pointer (the reference's TORCH_CHECKs) */
+    MIA_ECUDA = -2,      /* a CUDA runtime call or the launch failed */
+    MIA_EWORKSPACE = -3  /* workspace missing or too small */
+};
+
+typedef struct mia_ss_params {
+    /* ---- sizes (selective_scan_oflex.cpp:169-180) */
+    int32_t batch, dim, seqlen, dstate, n_groups, delta_dim;
+    int32_t itype;           /* dtype of u, delta, B, C, z and of du, ddelta, dB, dC, dz */
+    int32_t otype;           /* dtype of out/out_z (fwd) and of dout/out_saved (bwd): itype or MIA_F32 ("oflex") */
+    int32_t delta_softplus;  /* 0/1 */
+    int32_t n_chunks;        /* 3rd dim of x; must equal mia_ss_num_chunks(seqlen) */
+
+    /* ---- inputs */
+    const void *u;           /* (batch, dim, seqlen)            itype */
+    const void *delta;       /* (batch, delta_dim, seqlen)      itype; dim % delta_dim == 0 */
+    const void *A;           /* (dim, dstate)                   f32, any strides */
+    const void *B;           /* (batch, n_groups, dstate, seqlen) itype */
+    const void *C;           /* same */
+    const void *D;           /* (dim) f32 contiguous, or NULL */
+    const void *delta_bias;  /* (delta_dim) f32 contiguous, or NULL */
+    const void *z;           /* (batch, dim, seqlen) itype, or NULL (mamba_ssm gate: out_z = out * silu(z)) */
+    int64_t u_batch_stride, u_d_stride;
+    int64_t delta_batch_stride, delta_d_stride;
+    int64_t A_d_stride, A_dstate_stride;
+    int64_t B_batch_stride, B_group_stride, B_dstate_stride;
+    int64_t C_batch_stride, C_group_stride, C_dstate_stride;
+    int64_t z_batch_stride, z_d_stride;
+
+    /* ---- forward outputs */
+    void *out;               /* (batch, dim, seqlen) otype : y + D*u (before the gate) */
+    void *out_z;             /* (batch, dim, seqlen) otype, required iff z != NULL */
+    float *x;                /* (batch, dim, n_chunks, 2*dstate) f32 contiguous: per-chunk (prod a, h) checkpoints;
+                                x[:, :, -1, 1::2] is the last state (test_selective_scan.py:79). Written by fwd,
+                                read by bwd when n_chunks > 1. */
+    int64_t out_batch_stride, out_d_stride;
+    int64_t out_z_batch_stride, out_z_d_stride;
+
+    /* ---- backward inputs */
+    const void *dout;        /* (batch, dim, seqlen) otype: grad of out (z == NULL) or of out_z (z != NULL) */
+    const void *out_saved;   /* fwd `out`, otype; required iff z != NULL */
+    int64_t dout_batch_stride, dout_d_stride;
+    int64_t out_saved_batch_stride, out_saved_d_stride;
+
+    /* ---- backward outputs (all fully overwritten, no pre-zeroing needed) */
+    void *du;                /* (batch, dim, seqlen) itype */
+    void *ddelta;            /* (batch, delta_dim, seqlen) itype (already summed over the delta group) */
+    float *dA;               /* (dim, dstate) f32 */
+    void *dB, *dC;           /* (batch, n_groups, dstate, seqlen) itype */
+    float *dD;               /* (dim) f32, required iff D != NULL */
+    float *ddelta_bias;      /* (delta_dim) f32, required iff delta_bias != NULL */
+    void *dz;                /* (batch, dim, seqlen) itype, required iff z != NULL */
+    int64_t du_batch_stride, du_d_stride;
+    int64_t ddelta_batch_stride, ddelta_d_stride;
+    int64_t dA_d_stride, dA_dstate_stride;
+    int64_t dB_batch_stride, dB_group_stride, dB_dstate_stride;
+    int64_t dC_batch_stride, dC_group_stride, dC_dstate_stride;
+    int64_t dz_batch_stride, dz_d_stride;
+
+    /* ---- scratch for the deterministic reductions of the backward (f32 partials) */
+    void *workspace;
+    size_t workspace_bytes;
+} mia_ss_params;
+
+/* ABI / build identification. */
+int mia_abi_version(void);
+const char *mia_last_error(void);
+
+/* Checkpoint geometry: tokens per chunk for a sequence length, and ceil(seqlen / chunk). */
+int mia_ss_chunk_len(int seqlen);
+int mia_ss_num_chunks(int seqlen);
+
+/* Forward.  Replaces selective_scan_fwd (selective_scan_oflex.cpp:143-231). */
+int mia_selective_scan_fwd(const mia_ss_params *p, void *cuda_stream);
+
+/* Bytes of workspace the backward needs for these sizes (only sizes/dtypes/optional-pointer presence are read). */
+size_t mia_selective_scan_bwd_workspace(const mia_ss_params *p);
+
+/* Backward.  Replaces selective_scan_bwd (selective_scan_oflex.cpp:233-355) including its post-kernel
+ * casts (:347) and delta-group folds (:348-353). */
+int mia_selective_scan_bwd(const mia_ss_params *p, void *cuda_stream);
+
+/* Number of kernel launches issued by this library on the calling thread since load (bench.py's gpu_launches). */
+uint64_t mia_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIA_SELECTIVE_SCAN_H_ */

@@ -1,0 +1,402 @@
+// Host side of libmia_scan.so: argument validation (the reference's TORCH_CHECKs,
+// selective_scan_oflex.cpp:152-204 / 245-312), tile planning, launches, the finalize kernel that folds the
+// backward's deterministic partials, and the extern "C" surface declared in include/mia_selective_scan.h.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/mia_selective_scan.h"
+#include "scan_common.cuh"
+
+namespace mia {
+template <typename T> cudaError_t launch_fwd(const ScanArgs &, int, cudaStream_t);
+template <typename T> cudaError_t launch_bwd(const ScanArgs &, int, cudaStream_t);
+}  // namespace mia
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define MIA_CHECK(cond, ...) \
+    do { if (!(cond)) return fail(MIA_EINVAL, __VA_ARGS__); } while (0)
+#define MIA_CUDA(expr) \
+    do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return fail(MIA_ECUDA, "%s: %s", #expr, cudaGetErrorString(e__)); } while (0)
+
+int esize(int dt) { return dt == MIA_F32 ? 4 : 2; }
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct DeviceInfo { int sms = 0; int smem_optin = 0; };
+int device_info(DeviceInfo &di) {
+    static thread_local int cached_dev = -1;
+    static thread_local DeviceInfo cached;
+    int dev = 0;
+    MIA_CUDA(cudaGetDevice(&dev));
+    if (dev != cached_dev) {
+        MIA_CUDA(cudaDeviceGetAttribute(&cached.sms, cudaDevAttrMultiProcessorCount, dev));
+        MIA_CUDA(cudaDeviceGetAttribute(&cached.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        cached_dev = dev;
+    }
+    di = cached;
+    return MIA_OK;
+}
+
+int lanes_per_row(int L) {
+    if (L > 128) return 32;
+    int need = (L + mia::kTok - 1) / mia::kTok, lpr = 4;
+    while (lpr < need) lpr <<= 1;
+    return lpr;
+}
+
+struct WorkspaceLayout {
+    size_t part_dA = 0, part_dD = 0, part_dbias = 0, acc_dB = 0, acc_dC = 0, ddelta_full = 0, total = 0;
+    size_t acc_bytes = 0;
+    bool bc_atomic = false;
+};
+
+// Tile plan shared by fwd and bwd (the checkpoint geometry must match between them).
+struct Plan {
+    int LPR, CH, n_chunks, RPP, NW, RT, tiles_per_group, n_items;
+};
+
+Plan make_plan(const mia_ss_params &p, int sms) {
+    Plan pl;
+    pl.LPR = lanes_per_row(p.seqlen);
+    pl.CH = pl.LPR * mia::kTok;
+    pl.n_chunks = (p.seqlen + pl.CH - 1) / pl.CH;
+    pl.RPP = 32 / pl.LPR;
+    pl.NW = 15;  // + 1 producer warp = 512 threads: 4 warps per SM sub-partition, 128 registers each
+    const int rows_per_group = p.dim / p.n_groups;
+    int rows_per_warp = 2;
+    int RT = pl.NW * pl.RPP * rows_per_warp;
+    // enough items to balance the persistent grid; never more rows than the group has; bound carry arrays
+    auto items = [&](int rt) { return (long long)p.batch * p.n_groups * ((rows_per_group + rt - 1) / rt); };
+    while (RT > pl.RPP && (items(RT) < 4LL * sms || RT * p.dstate > 8192)) RT >>= 1;
+    if (RT > rows_per_group) RT = round_up(rows_per_group, pl.RPP);
+    if (RT < 1) RT = 1;
+    pl.RT = RT;
+    pl.tiles_per_group = (rows_per_group + RT - 1) / RT;
+    pl.n_items = p.batch * p.n_groups * pl.tiles_per_group;
+    return pl;
+}
+
+WorkspaceLayout workspace_layout(const mia_ss_params &p, const Plan &pl) {
+    WorkspaceLayout w;
+    auto take = [&](size_t nfloat) { size_t off = w.total; w.total += (nfloat * 4 + 255) / 256 * 256; return off; };
+    w.bc_atomic = p.dstate > 2;
+    w.part_dA = take((size_t)p.batch * p.dim * p.dstate);
+    w.part_dD = take((size_t)p.batch * p.dim);
+    w.part_dbias = take((size_t)p.batch * p.dim);
+    size_t nacc = w.bc_atomic ? (size_t)p.batch * p.n_groups * p.dstate * ((p.seqlen + 3) & ~3)
+                              : (size_t)pl.n_items * p.dstate * p.seqlen;
+    w.acc_dB = take(nacc);
+    w.acc_dC = take(nacc);
+    w.acc_bytes = nacc * 4;
+    if (p.dim != p.delta_dim) w.ddelta_full = take((size_t)p.batch * p.dim * p.seqlen);
+    return w;
+}
+
+int validate_common(const mia_ss_params &p) {
+    MIA_CHECK(p.itype == MIA_F32 || p.itype == MIA_F16 || p.itype == MIA_BF16, "u must be float32, float16 or bfloat16");
+    MIA_CHECK(p.otype == p.itype || p.otype == MIA_F32, "out/dout dtype must be the input dtype or float32");
+    MIA_CHECK(p.batch > 0 && p.dim > 0 && p.seqlen > 0 && p.dstate > 0 && p.n_groups > 0 && p.delta_dim > 0, "empty or negative size");
+    MIA_CHECK(p.dim % p.n_groups == 0, "dims should be dividable by n_groups");
+    MIA_CHECK(p.dim % p.delta_dim == 0, "dims should be dividable by delta_dim");
+    MIA_CHECK(p.dstate <= 256, "selective_scan only supports state dimension <= 256");
+    MIA_CHECK(p.u && p.delta && p.A && p.B && p.C, "u, delta, A, B, C must not be null");
+    MIA_CHECK(p.n_chunks == mia_ss_num_chunks(p.seqlen), "x must have %d chunks for seqlen %d (got %d)", mia_ss_num_chunks(p.seqlen),
+              p.seqlen, p.n_chunks);
+    MIA_CHECK((long long)p.batch * p.dim < (1LL << 31) / 2, "batch*dim too large");
+    return MIA_OK;
+}
+
+void fill_common(mia::ScanArgs &a, const mia_ss_params &p, const Plan &pl, bool bwd) {
+    memset(&a, 0, sizeof(a));
+    a.batch = p.batch; a.dim = p.dim; a.L = p.seqlen; a.N = p.dstate; a.G = p.n_groups; a.delta_dim = p.delta_dim;
+    a.rows_per_group = p.dim / p.n_groups;
+    a.delta_ratio = p.dim / p.delta_dim;
+    a.softplus = p.delta_softplus; a.has_z = p.z != nullptr; a.out_f32 = (p.otype == MIA_F32) && (p.itype != MIA_F32);
+    a.RT = pl.RT; a.tiles_per_group = pl.tiles_per_group; a.LPR = pl.LPR; a.CH = pl.CH; a.n_chunks = pl.n_chunks;
+    a.n_items = pl.n_items; a.n_consumer_warps = pl.NW;
+    a.u = p.u; a.delta = p.delta; a.A = p.A; a.B = p.B; a.C = p.C; a.D = p.D; a.delta_bias = p.delta_bias; a.z = p.z;
+    a.x = p.x;
+    a.u_bs = p.u_batch_stride; a.u_ds = p.u_d_stride; a.delta_bs = p.delta_batch_stride; a.delta_ds = p.delta_d_stride;
+    a.z_bs = p.z_batch_stride; a.z_ds = p.z_d_stride; a.A_ds = p.A_d_stride; a.A_ns = p.A_dstate_stride;
+    a.B_bs = p.B_batch_stride; a.B_gs = p.B_group_stride; a.B_ns = p.B_dstate_stride;
+    a.C_bs = p.C_batch_stride; a.C_gs = p.C_group_stride; a.C_ns = p.C_dstate_stride;
+    const bool whole = pl.n_chunks == 1;
+    a.flat_u = whole && p.u_d_stride == p.seqlen;
+    a.flat_delta = whole && p.delta_d_stride == p.seqlen;
+    a.flat_z = a.has_z && whole && p.z_d_stride == p.seqlen;
+    a.flat_B = whole && p.B_dstate_stride == p.seqlen;
+    a.flat_C = whole && p.C_dstate_stride == p.seqlen;
+    (void)bwd;
+}
+
+// Shared-memory carve-up.  Returns false if not even two stages fit.
+bool layout_smem(mia::ScanArgs &a, int es, int eso, bool bwd, int smem_max) {
+    const int span = a.CH < a.L ? a.CH : a.L;
+    a.row_pitch = round_up(span * es, 16) + 16;
+    a.rowo_pitch = round_up(span * eso, 16) + 16;
+    a.bc_pitch = a.row_pitch;
+    const int slack = a.CH * 4 + 16;
+    int off = 0;
+    auto region = [&](int rows, int pitch) { int o = off; off += round_up(rows * pitch + slack, 128); return o; };
+    a.off_u = region(a.RT, a.row_pitch);
+    a.off_delta = region(a.RT, a.row_pitch);
+    if (a.has_z) a.off_z = region(a.RT, a.row_pitch);
+    if (bwd) {
+        a.off_dout = region(a.RT, a.rowo_pitch);
+        if (a.has_z) a.off_osaved = region(a.RT, a.rowo_pitch);
+    }
+    a.off_B = region(a.N, a.bc_pitch);
+    a.off_C = region(a.N, a.bc_pitch);
+    a.stage_bytes = off;
+    int fixed = 0;
+    const int bars = 2 * mia::kMaxStages * 8;
+    int carry = bwd ? (2 * a.RT * a.N + 2 * a.RT) * 4 : a.RT * a.N * 8;
+    carry = round_up(carry, 128);
+    const int red = bwd ? a.n_consumer_warps * 256 * 4 : 0;
+    fixed = round_up(bars, 128) + carry + red;
+    int stages = (smem_max - fixed) / a.stage_bytes;
+    if (stages > mia::kMaxStages) stages = mia::kMaxStages;
+    if (stages < 2) return false;
+    a.stages = stages;
+    a.off_bars = stages * a.stage_bytes;
+    a.off_carry = a.off_bars + round_up(bars, 128);
+    a.off_red = a.off_carry + carry;
+    a.smem_bytes = a.off_red + red;
+    return true;
+}
+
+// Pick the tile plan and carve shared memory; halves the row tile until at least two stages fit.
+int plan_and_layout(const mia_ss_params &p, const DeviceInfo &di, bool bwd, Plan &pl, mia::ScanArgs &a) {
+    pl = make_plan(p, di.sms);
+    const int es = esize(p.itype), eso = esize(p.otype);
+    for (;;) {
+        fill_common(a, p, pl, bwd);
+        if (bwd) {
+            const bool whole = pl.n_chunks == 1;
+            a.flat_dout = whole && p.dout_d_stride == p.seqlen;
+            a.flat_osaved = a.has_z && whole && p.out_saved_d_stride == p.seqlen;
+        }
+        if (layout_smem(a, es, eso, bwd, di.smem_optin)) return MIA_OK;
+        MIA_CHECK(pl.RT > pl.RPP, "tile does not fit in shared memory (dstate %d, seqlen %d)", p.dstate, p.seqlen);
+        pl.RT = pl.RT / 2 < pl.RPP ? pl.RPP : pl.RT / 2;
+        pl.tiles_per_group = (p.dim / p.n_groups + pl.RT - 1) / pl.RT;
+        pl.n_items = p.batch * p.n_groups * pl.tiles_per_group;
+    }
+}
+
+template <typename F>
+int dispatch(int itype, F &&f) {
+    switch (itype) {
+        case MIA_F32: return f((float *)nullptr);
+        case MIA_F16: return f((__half *)nullptr);
+        default: return f((__nv_bfloat16 *)nullptr);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Finalize: fold the backward's partials in a fixed order (deterministic) and cast to the output dtypes.
+struct FinArgs {
+    int batch, dim, L, N, G, delta_dim, ratio, tiles, bc_atomic, Lp, has_D, has_bias;
+    const float *part_dA, *part_dD, *part_dbias, *acc_dB, *acc_dC, *ddelta_full;
+    float *dA, *dD, *dbias;
+    void *dB, *dC, *ddelta;
+    long long dA_ds, dA_ns, dB_bs, dB_gs, dB_ns, dC_bs, dC_gs, dC_ns, dd_bs, dd_ds;
+    long long n_bc, n_dA, n_dD, n_db, n_dd;
+};
+
+template <typename T>
+__global__ void ss_finalize_kernel(const __grid_constant__ FinArgs f) {
+    using raw = typename mia::Cvt<T>::raw;
+    const long long total = 2 * f.n_bc + f.n_dA + f.n_dD + f.n_db + f.n_dd;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        long long i = idx;
+        if (i < 2 * f.n_bc) {
+            const bool isC = i >= f.n_bc;
+            if (isC) i -= f.n_bc;
+            const int l = (int)(i % f.L);
+            long long t = i / f.L;
+            const int n = (int)(t % f.N); t /= f.N;
+            const int g = (int)(t % f.G);
+            const int b = (int)(t / f.G);
+            const float *acc = isC ? f.acc_dC : f.acc_dB;
+            float sum = 0.f;
+            if (f.bc_atomic) {
+                sum = acc[((size_t)(b * f.G + g) * f.N + n) * f.Lp + l];
+            } else {
+                for (int tl = 0; tl < f.tiles; ++tl) sum += acc[(((size_t)(b * f.G + g) * f.tiles + tl) * f.N + n) * f.L + l];
+            }
+            raw *dst = reinterpret_cast<raw *>(isC ? f.dC : f.dB);
+            const long long o = isC ? (b * f.dC_bs + g * f.dC_gs + n * f.dC_ns + l) : (b * f.dB_bs + g * f.dB_gs + n * f.dB_ns + l);
+            dst[o] = mia::Cvt<T>::from_f(sum);
+            continue;
+        }
+        i -= 2 * f.n_bc;
+        if (i < f.n_dA) {
+            const int n = (int)(i % f.N), d = (int)(i / f.N);
+            float sum = 0.f;
+            for (int b = 0; b < f.batch; ++b) sum += f.part_dA[((size_t)b * f.dim + d) * f.N + n];
+            f.dA[d * f.dA_ds + n * f.dA_ns] = sum;
+            continue;
+        }
+        i -= f.n_dA;
+        if (i < f.n_dD) {
+            float sum = 0.f;
+            for (int b = 0; b < f.batch; ++b) sum += f.part_dD[(size_t)b * f.dim + i];
+            f.dD[i] = sum;
+            continue;
+        }
+        i -= f.n_dD;
+        if (i < f.n_db) {
+            float sum = 0.f;
+            for (int b = 0; b < f.batch; ++b)
+                for (int r = 0; r < f.ratio; ++r) sum += f.part_dbias[(size_t)b * f.dim + i * f.ratio + r];
+            f.dbias[i] = sum;
+            continue;
+        }
+        i -= f.n_db;
+        {   // ddelta fold over the delta group (selective_scan_oflex.cpp:348-350)
+            const int l = (int)(i % f.L);
+            long long t = i / f.L;
+            const int dg = (int)(t % f.delta_dim);
+            const int b = (int)(t / f.delta_dim);
+            float sum = 0.f;
+            for (int r = 0; r < f.ratio; ++r) sum += f.ddelta_full[((size_t)b * f.dim + dg * f.ratio + r) * f.L + l];
+            reinterpret_cast<raw *>(f.ddelta)[b * f.dd_bs + dg * f.dd_ds + l] = mia::Cvt<T>::from_f(sum);
+        }
+    }
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int mia_abi_version(void) { return MIA_ABI_VERSION; }
+const char *mia_last_error(void) { return g_err; }
+uint64_t mia_launch_count(void) { return g_launches.load(); }
+
+int mia_ss_chunk_len(int seqlen) { return lanes_per_row(seqlen) * mia::kTok; }
+int mia_ss_num_chunks(int seqlen) {
+    const int ch = mia_ss_chunk_len(seqlen);
+    return (seqlen + ch - 1) / ch;
+}
+
+int mia_selective_scan_fwd(const mia_ss_params *pp, void *cuda_stream) {
+    if (!pp) return fail(MIA_EINVAL, "null params");
+    const mia_ss_params &p = *pp;
+    if (int rc = validate_common(p)) return rc;
+    MIA_CHECK(p.out && p.x, "out and x must not be null");
+    MIA_CHECK(!p.z || p.out_z, "out_z is required when z is given");
+    DeviceInfo di;
+    if (int rc = device_info(di)) return rc;
+    Plan pl;
+    mia::ScanArgs a;
+    if (int rc = plan_and_layout(p, di, false, pl, a)) return rc;
+    a.out = p.out; a.out_z = p.out_z;
+    a.out_bs = p.out_batch_stride; a.out_ds = p.out_d_stride; a.outz_bs = p.out_z_batch_stride; a.outz_ds = p.out_z_d_stride;
+    const int grid = a.n_items < di.sms ? a.n_items : di.sms;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    const int rc = dispatch(p.itype, [&](auto *tag) {
+        using T = typename std::remove_pointer<decltype(tag)>::type;
+        return (int)mia::launch_fwd<T>(a, grid, stream);
+    });
+    if (rc != 0) return fail(MIA_ECUDA, "selective_scan_fwd launch: %s", cudaGetErrorString((cudaError_t)rc));
+    g_launches.fetch_add(1);
+    return MIA_OK;
+}
+
+size_t mia_selective_scan_bwd_workspace(const mia_ss_params *pp) {
+    if (!pp) return 0;
+    DeviceInfo di;
+    if (device_info(di) != MIA_OK) { di.sms = 148; di.smem_optin = 232448; }
+    Plan pl;
+    mia::ScanArgs a;
+    if (plan_and_layout(*pp, di, true, pl, a) != MIA_OK) return 0;
+    return workspace_layout(*pp, pl).total;
+}
+
+int mia_selective_scan_bwd(const mia_ss_params *pp, void *cuda_stream) {
+    if (!pp) return fail(MIA_EINVAL, "null params");
+    const mia_ss_params &p = *pp;
+    if (int rc = validate_common(p)) return rc;
+    MIA_CHECK(p.dout && p.du && p.ddelta && p.dA && p.dB && p.dC, "dout, du, ddelta, dA, dB, dC must not be null");
+    MIA_CHECK(!p.D || p.dD, "dD is required when D is given");
+    MIA_CHECK(!p.delta_bias || p.ddelta_bias, "ddelta_bias is required when delta_bias is given");
+    MIA_CHECK(!p.z || (p.dz && p.out_saved), "dz and out_saved are required when z is given");
+    MIA_CHECK(p.n_chunks == 1 || p.x, "x is required when the sequence spans more than one chunk");
+    DeviceInfo di;
+    if (int rc = device_info(di)) return rc;
+    Plan pl;
+    mia::ScanArgs a;
+    if (int rc = plan_and_layout(p, di, true, pl, a)) return rc;
+    a.dout = p.dout; a.out_saved = p.out_saved; a.du = p.du; a.ddelta = p.ddelta; a.dz = p.dz;
+    a.dout_bs = p.dout_batch_stride; a.dout_ds = p.dout_d_stride;
+    a.osaved_bs = p.out_saved_batch_stride; a.osaved_ds = p.out_saved_d_stride;
+    a.du_bs = p.du_batch_stride; a.du_ds = p.du_d_stride; a.dd_bs = p.ddelta_batch_stride; a.dd_ds = p.ddelta_d_stride;
+    a.dz_bs = p.dz_batch_stride; a.dz_ds = p.dz_d_stride;
+    const WorkspaceLayout w = workspace_layout(p, pl);
+    if (!p.workspace || p.workspace_bytes < w.total)
+        return fail(MIA_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total, p.workspace ? p.workspace_bytes : (size_t)0);
+    MIA_CHECK(((uintptr_t)p.workspace & 255) == 0, "workspace must be 256-byte aligned");
+    char *ws = (char *)p.workspace;
+    a.part_dA = (float *)(ws + w.part_dA); a.part_dD = (float *)(ws + w.part_dD); a.part_dbias = (float *)(ws + w.part_dbias);
+    a.acc_dB = (float *)(ws + w.acc_dB); a.acc_dC = (float *)(ws + w.acc_dC);
+    a.ddelta_full = (float *)(ws + w.ddelta_full);
+    a.bc_atomic = w.bc_atomic;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    if (w.bc_atomic) {
+        MIA_CUDA(cudaMemsetAsync(a.acc_dB, 0, w.acc_bytes, stream));
+        MIA_CUDA(cudaMemsetAsync(a.acc_dC, 0, w.acc_bytes, stream));
+        g_launches.fetch_add(2);
+    }
+    const int grid = a.n_items < di.sms ? a.n_items : di.sms;
+    int rc = dispatch(p.itype, [&](auto *tag) {
+        using T = typename std::remove_pointer<decltype(tag)>::type;
+        return (int)mia::launch_bwd<T>(a, grid, stream);
+    });
+    if (rc != 0) return fail(MIA_ECUDA, "selective_scan_bwd launch: %s", cudaGetErrorString((cudaError_t)rc));
+    g_launches.fetch_add(1);
+
+    FinArgs f;
+    memset(&f, 0, sizeof(f));
+    f.batch = p.batch; f.dim = p.dim; f.L = p.seqlen; f.N = p.dstate; f.G = p.n_groups; f.delta_dim = p.delta_dim;
+    f.ratio = p.dim / p.delta_dim; f.tiles = pl.tiles_per_group; f.bc_atomic = w.bc_atomic; f.Lp = (p.seqlen + 3) & ~3;
+    f.part_dA = a.part_dA; f.part_dD = a.part_dD; f.part_dbias = a.part_dbias; f.acc_dB = a.acc_dB; f.acc_dC = a.acc_dC;
+    f.ddelta_full = a.ddelta_full;
+    f.dA = p.dA; f.dD = p.dD; f.dbias = p.ddelta_bias; f.dB = p.dB; f.dC = p.dC; f.ddelta = p.ddelta;
+    f.dA_ds = p.dA_d_stride; f.dA_ns = p.dA_dstate_stride;
+    f.dB_bs = p.dB_batch_stride; f.dB_gs = p.dB_group_stride; f.dB_ns = p.dB_dstate_stride;
+    f.dC_bs = p.dC_batch_stride; f.dC_gs = p.dC_group_stride; f.dC_ns = p.dC_dstate_stride;
+    f.dd_bs = p.ddelta_batch_stride; f.dd_ds = p.ddelta_d_stride;
+    f.n_bc = (long long)p.batch * p.n_groups * p.dstate * p.seqlen;
+    f.n_dA = (long long)p.dim * p.dstate;
+    f.n_dD = p.D ? p.dim : 0;
+    f.n_db = p.delta_bias ? p.delta_dim : 0;
+    f.n_dd = f.ratio > 1 ? (long long)p.batch * p.delta_dim * p.seqlen : 0;
+    const long long total = 2 * f.n_bc + f.n_dA + f.n_dD + f.n_db + f.n_dd;
+    long long blocks = (total + 255) / 256;
+    if (blocks > di.sms * 8) blocks = di.sms * 8;
+    rc = dispatch(p.itype, [&](auto *tag) {
+        using T = typename std::remove_pointer<decltype(tag)>::type;
+        ss_finalize_kernel<T><<<(int)blocks, 256, 0, stream>>>(f);
+        return (int)cudaGetLastError();
+    });
+    if (rc != 0) return fail(MIA_ECUDA, "selective_scan_bwd finalize launch: %s", cudaGetErrorString((cudaError_t)rc));
+    g_launches.fetch_add(1);
+    return MIA_OK;
+}
+
+}  // extern "C"

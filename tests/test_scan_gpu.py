@@ -1,0 +1,171 @@
+"""GPU parity: the CUDA selective scan (through the C ABI) against the CPU oracle on the same seeded inputs."""
+import itertools
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(seed, batch, dim, L, N, G, ddim, has_D, has_z, has_bias, dtype, dev="cuda"):
+    """Reference generators (test_selective_scan.py:409-444)."""
+    g = torch.Generator().manual_seed(seed)
+    A = -0.5 * torch.rand(dim, N, generator=g)
+    B = torch.randn(batch, G, N, L, generator=g).to(dtype)
+    C = torch.randn(batch, G, N, L, generator=g).to(dtype)
+    D = torch.randn(dim, generator=g) if has_D else None
+    z = torch.randn(batch, dim, L, generator=g).to(dtype) if has_z else None
+    bias = 0.5 * torch.rand(ddim, generator=g) if has_bias else None
+    u = torch.randn(batch, dim, L, generator=g).to(dtype)
+    delta = (0.5 * torch.rand(batch, ddim, L, generator=g)).to(dtype)
+    dout = torch.randn(batch, dim, L, generator=g).to(dtype)
+    cpu = dict(u=u, delta=delta, A=A, B=B, C=C, D=D, z=z, delta_bias=bias, dout=dout)
+    gpu = {k: (None if v is None else v.to(dev)) for k, v in cpu.items()}
+    return cpu, gpu
+
+
+def _cmp(got, ref, rtol, atol, what):
+    got, ref = got.detach().float().cpu(), ref.float()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    assert torch.isfinite(got).all(), f"{what}: non-finite values"
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = err > tol
+    assert not bool(bad.any()), (f"{what}: {int(bad.sum())}/{bad.numel()} out of tolerance, max err {err.max().item():.3e} "
+                                 f"(ref max {ref.abs().max().item():.3e})")
+
+
+def _run_case(batch, dim, L, N, G, ddim, has_D, has_z, has_bias, softplus, dtype, out_float, seed=0):
+    from medical_image_analysis_b200 import scan_bwd, scan_fwd
+    from oracle import ss_ref_c
+    cpu, gpu = _inputs(seed, batch, dim, L, N, G, ddim, has_D, has_z, has_bias, dtype)
+    out, x, out_z = scan_fwd(gpu["u"], gpu["delta"], gpu["A"], gpu["B"], gpu["C"], gpu["D"], gpu["z"], gpu["delta_bias"],
+                             softplus, out_float)
+    r_out, r_out_z, r_last = ss_ref_c.fwd(cpu["u"], cpu["delta"], cpu["A"], cpu["B"], cpu["C"], cpu["D"], cpu["z"],
+                                          cpu["delta_bias"], softplus)
+    lowp = dtype != torch.float32
+    # fp32 (and fp32 "oflex" outputs of low-precision inputs): 1e-5-class; outputs stored in bf16/fp16: one rounding
+    o_rt, o_at = (1e-5, 2e-5) if (not lowp or out_float) else ((8e-3, 8e-3) if dtype == torch.bfloat16 else (1e-3, 1e-3))
+    scale = max(1.0, r_out.abs().max().item())
+    _cmp(out, r_out, o_rt, o_at * scale, "out")
+    if has_z:
+        _cmp(out_z, r_out_z, o_rt, o_at * scale, "out_z")
+    _cmp(x[:, :, -1, 1::2], r_last, 1e-5, 2e-5 * max(1.0, r_last.abs().max().item()), "last_state")
+
+    dout = gpu["dout"].float() if out_float else gpu["dout"]
+    du, dd, dA, dB, dC, dD, dbias, dz = scan_bwd(gpu["u"], gpu["delta"], gpu["A"], gpu["B"], gpu["C"], gpu["D"], gpu["z"],
+                                                 gpu["delta_bias"], dout, x, out if has_z else None, softplus)
+    # with z the CUDA path reads the saved `out` (rounded to the output dtype), like mamba_ssm does
+    ref = ss_ref_c.bwd(cpu["u"], cpu["delta"], cpu["A"], cpu["B"], cpu["C"], cpu["D"], cpu["z"], cpu["delta_bias"],
+                       cpu["dout"], softplus)
+    g_rt, g_at = (2e-5, 2e-5) if not lowp else ((1e-2, 1e-2) if dtype == torch.bfloat16 else (2e-3, 2e-3))
+    if has_z and lowp and not out_float:
+        g_rt, g_at = g_rt * 2, g_at * 2
+    for name, got in (("du", du), ("ddelta", dd), ("dB", dB), ("dC", dC), ("dz", dz)):
+        if got is not None:
+            s = max(1.0, ref[name].abs().max().item())
+            _cmp(got, ref[name], g_rt, g_at * s, name)
+    for name, got in (("dA", dA), ("dD", dD), ("ddelta_bias", dbias)):   # fp32 weight grads
+        if got is not None:
+            s = max(1.0, ref[name].abs().max().item())
+            w_rt, w_at = (2e-5, 2e-5) if not (has_z and lowp and not out_float) else (1e-2, 1e-2)
+            _cmp(got, ref[name], w_rt, w_at * s, name)
+
+
+SMALL = [
+    # batch, dim, L, N, G, ddim
+    (2, 8, 64, 1, 1, 8), (2, 8, 37, 1, 2, 8), (2, 8, 37, 4, 2, 2), (1, 12, 49, 16, 1, 12), (2, 16, 70, 16, 4, 16),
+    (2, 6, 1, 2, 1, 6), (1, 4, 7, 3, 1, 4), (2, 33, 196, 1, 3, 33), (1, 8, 197, 16, 1, 8), (2, 8, 256, 2, 2, 4),
+    (1, 8, 257, 1, 1, 8), (1, 5, 600, 4, 1, 5), (1, 4, 1100, 1, 2, 4), (1, 3, 2049, 2, 1, 3),
+]
+
+
+@pytest.mark.parametrize("shape", SMALL, ids=[f"b{s[0]}d{s[1]}L{s[2]}N{s[3]}G{s[4]}dd{s[5]}" for s in SMALL])
+@pytest.mark.parametrize("dtype,out_float", [(torch.float32, False), (torch.bfloat16, False), (torch.bfloat16, True),
+                                             (torch.float16, False)], ids=["f32", "bf16", "bf16o32", "f16"])
+def test_scan_parity_small(shape, dtype, out_float):
+    batch, dim, L, N, G, ddim = shape
+    _run_case(batch, dim, L, N, G, ddim, True, False, True, True, dtype, out_float)
+
+
+@pytest.mark.parametrize("has_D,has_z,has_bias,softplus", list(itertools.product([False, True], repeat=4)))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_scan_parity_flags(has_D, has_z, has_bias, softplus, dtype):
+    _run_case(2, 16, 100, 4, 2, 16, has_D, has_z, has_bias, softplus, dtype, False, seed=3)
+
+
+def test_scan_golden_reference_vectors():
+    """CUDA path vs the vectors produced by the reference's own selective_scan_ref + autograd (tests/golden)."""
+    from medical_image_analysis_b200 import scan_bwd, scan_fwd
+    from tests.golden_util import scan_cases
+    for case in scan_cases():
+        i, ref = case["inp"], case["ref"]
+        g = {k: (None if v is None else v.cuda()) for k, v in i.items()}
+        out, x, out_z = scan_fwd(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], g["z"], g["delta_bias"], case["softplus"], False)
+        final = out_z if g["z"] is not None else out
+        lowp = case["dtype"] != torch.float32
+        rt, at = (2e-2, 2e-2) if lowp else (2e-5, 2e-5)
+        _cmp(final, ref["out"], rt, at * max(1.0, ref["out"].abs().max().item()), case["tag"] + ".out")
+        _cmp(x[:, :, -1, 1::2], ref["last_state"], 2e-5, 2e-5, case["tag"] + ".last_state")
+        grads = scan_bwd(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], g["z"], g["delta_bias"], g["dout"], x,
+                         out if g["z"] is not None else None, case["softplus"])
+        names = ("du", "ddelta", "dA", "dB", "dC", "dD", "ddelta_bias", "dz")
+        for name, got in zip(names, grads):
+            if got is not None:
+                rt, at = (3e-2, 3e-2) if lowp else (2e-4, 2e-4)
+                _cmp(got, ref[name], rt, at * max(1.0, ref[name].abs().max().item()), f"{case['tag']}.{name}")
+
+
+def test_c1_config():
+    """BASELINE.json configs[0] (B=2, L=196, D=192, d_state=16, fp32) against the reference's stored outputs."""
+    from medical_image_analysis_b200 import scan_bwd, scan_fwd
+    from tests.golden_util import c1_case
+    inp, ref = c1_case()
+    g = {k: (None if v is None else v.cuda()) for k, v in inp.items()}
+    out, x, _ = scan_fwd(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], None, g["delta_bias"], True, False)
+    _cmp(out, ref["out"], 1e-4, 1e-4, "out")
+    grads = scan_bwd(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], None, g["delta_bias"], g["dout"], x, None, True)
+    for name, got in zip(("du", "ddelta", "dA", "dB", "dC", "dD", "ddelta_bias"), grads):
+        _cmp(got, ref[name], 1e-3, 1e-4 * max(1.0, ref[name].abs().max().item()), name)
+
+
+@pytest.mark.parametrize("N", [1, 16])
+def test_scan_m196_shape(N):
+    """The metric's shape (R=3072 rows, G=4, L=196) at a batch the C oracle finishes in seconds."""
+    _run_case(2, 3072, 196, N, 4, 3072, True, False, True, True, torch.bfloat16, True, seed=11)
+
+
+def test_scan_strided_inputs():
+    """Only the last dim must be contiguous (selective_scan_oflex.cpp:167-168): row / batch strides are free."""
+    from medical_image_analysis_b200 import scan_fwd
+    from oracle import ss_ref_c
+    cpu, gpu = _inputs(5, 2, 8, 50, 2, 1, 8, True, False, True, torch.float32)
+    big = torch.zeros(2, 8, 77, device="cuda")
+    big[:, :, 3:53] = gpu["u"]
+    u_view = big[:, :, 3:53]
+    assert not u_view.is_contiguous()
+    out, x, _ = scan_fwd(u_view, gpu["delta"], gpu["A"].t().contiguous().t(), gpu["B"], gpu["C"], gpu["D"], None, gpu["delta_bias"], True, False)
+    r_out, _, _ = ss_ref_c.fwd(cpu["u"], cpu["delta"], cpu["A"], cpu["B"], cpu["C"], cpu["D"], None, cpu["delta_bias"], True)
+    _cmp(out, r_out, 1e-5, 2e-5 * max(1.0, r_out.abs().max().item()), "out")
+
+
+def test_bwd_is_deterministic_dstate1():
+    from medical_image_analysis_b200 import scan_bwd, scan_fwd
+    _, g = _inputs(9, 4, 96, 300, 1, 2, 96, True, False, True, torch.bfloat16)
+    out, x, _ = scan_fwd(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], None, g["delta_bias"], True, True)
+    a = scan_bwd(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], None, g["delta_bias"], g["dout"].float(), x, None, True)
+    b = scan_bwd(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], None, g["delta_bias"], g["dout"].float(), x, None, True)
+    for ta, tb in zip(a, b):
+        if ta is not None:
+            assert torch.equal(ta, tb)
+
+
+def test_errors_are_raised():
+    from medical_image_analysis_b200 import scan_fwd
+    _, g = _inputs(1, 1, 4, 16, 1, 1, 4, False, False, False, torch.float32)
+    with pytest.raises(RuntimeError):
+        scan_fwd(g["u"], g["delta"], g["A"].double(), g["B"], g["C"])
+    with pytest.raises(RuntimeError):
+        scan_fwd(g["u"], g["delta"][:, :3], g["A"], g["B"], g["C"])
+    with pytest.raises(RuntimeError):
+        scan_fwd(g["u"].transpose(1, 2).contiguous().transpose(1, 2), g["delta"], g["A"], g["B"], g["C"])
