@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: SS2D selective scan forward+backward, patch-tokens/s and % of the HBM roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME] [--no-extras]
+
+A step = one forward + one backward of the selective-scan op over one synthetic batch with SS2D's shapes
+(d_inner 768 -> R = 4*768 = 3072 scan rows, G = 4 B/C groups).  One patch-token = one (image, position) over
+all R rows.  `value` is measured with inputs resident in HBM; `e2e` goes through the same C-ABI calls but
+starts from pinned HOST buffers and ends with the results back in host memory (copies inside the timed region).
+N > 1 (torchrun): pure data parallelism, per-GPU batch fixed (weak scaling), NCCL all-reduce of the parameter
+gradients (dA, dD, d_delta_bias) every step -- the scan itself has no collective (multi-GPU).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# name -> batch, rows, groups, L, d_state, out_f32 ("oflex": fp32 out / dout)
+WORKLOADS = {
+    "ss2d_m196_n1": dict(B=64, R=3072, G=4, L=196, N=1, out_f32=False),
+    "ss2d_m196_n16": dict(B=64, R=3072, G=4, L=196, N=16, out_f32=False),
+    "ss2d_m6400_n1": dict(B=4, R=3072, G=4, L=6400, N=1, out_f32=False),
+    "ss2d_m6400_n16": dict(B=4, R=3072, G=4, L=6400, N=16, out_f32=False),
+    "ss2d_m196_n1_o32": dict(B=64, R=3072, G=4, L=196, N=1, out_f32=True),
+    "ss2d_m196_n16_o32": dict(B=64, R=3072, G=4, L=196, N=16, out_f32=True),
+}
+DEFAULT = "ss2d_m196_n1"
+METRIC = "patch-tokens/sec SS2D fwd+bwd at L=196/6400 D=768; % HBM roofline"
+
+
+def bytes_per_token(w, es=2):
+    """Algorithmic HBM bytes per patch-token: every activation read/written exactly once."""
+    R, G, N = w["R"], w["G"], w["N"]
+    eso = 4 if w["out_f32"] else es
+    fwd = (2 * R + 2 * G * N) * es + R * eso
+    bwd = (2 * R + 2 * G * N) * es + R * eso + 2 * R * es + 2 * G * N * es
+    return fwd, bwd
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_inputs(w, device, seed=0, dtype=torch.bfloat16):
+    """Reference generators (test_selective_scan.py:409-444)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    B, R, G, L, N = w["B"], w["R"], w["G"], w["L"], w["N"]
+    A = -0.5 * torch.rand(R, N, generator=g)
+    D = torch.randn(R, generator=g)
+    bias = 0.5 * torch.rand(R, generator=g)
+    gd = torch.Generator(device=device).manual_seed(seed)
+    Bm = torch.randn(B, G, N, L, generator=gd, device=device).to(dtype)
+    C = torch.randn(B, G, N, L, generator=gd, device=device).to(dtype)
+    u = torch.randn(B, R, L, generator=gd, device=device).to(dtype)
+    delta = (0.5 * torch.rand(B, R, L, generator=gd, device=device)).to(dtype)
+    dout = torch.randn(B, R, L, generator=gd, device=device).to(torch.float32 if w["out_f32"] else dtype)
+    return dict(u=u, delta=delta, A=A.to(device), B=Bm, C=C, D=D.to(device), bias=bias.to(device), dout=dout)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path).read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def run_device_steps(inp, steps, warmup, dist_grads=None):
+    """K timed fwd+bwd steps on resident inputs; returns (total_ms, fwd_ms_avg, bwd_ms_avg)."""
+    from medical_image_analysis_b200 import scan_bwd, scan_fwd
+    out_f32 = inp["dout"].dtype == torch.float32 and inp["u"].dtype != torch.float32
+
+    def one(ev=None):
+        if ev:
+            ev[0].record()
+        out, x, _ = scan_fwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], None, inp["bias"], True, out_f32)
+        if ev:
+            ev[1].record()
+        g = scan_bwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], None, inp["bias"], inp["dout"], x, None, True)
+        if dist_grads is not None:
+            dist_grads(g)
+        if ev:
+            ev[2].record()
+        return out, g
+
+    for _ in range(warmup):
+        one()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    torch.cuda.synchronize()
+    for k in range(steps):
+        one(evs[k])
+    torch.cuda.synchronize()
+    total = evs[0][0].elapsed_time(evs[-1][2])
+    fwd = sum(e[0].elapsed_time(e[1]) for e in evs) / steps
+    bwd = sum(e[1].elapsed_time(e[2]) for e in evs) / steps
+    return total, fwd, bwd
+
+
+def run_e2e_steps(w, inp, steps, warmup):
+    """Same calls, but every step starts from pinned host buffers and ends with the results in host memory."""
+    from medical_image_analysis_b200 import scan_bwd, scan_fwd
+    out_f32 = w["out_f32"]
+    host_in = {k: inp[k].cpu().pin_memory() for k in ("u", "delta", "B", "C", "dout")}
+    dev_in = {k: torch.empty_like(inp[k]) for k in host_in}
+    h2d = sum(t.numel() * t.element_size() for t in host_in.values())
+    host_out = None
+    d2h = 0
+
+    def one():
+        nonlocal host_out, d2h
+        for k in host_in:
+            dev_in[k].copy_(host_in[k], non_blocking=True)
+        out, x, _ = scan_fwd(dev_in["u"], dev_in["delta"], inp["A"], dev_in["B"], dev_in["C"], inp["D"], None, inp["bias"], True, out_f32)
+        g = scan_bwd(dev_in["u"], dev_in["delta"], inp["A"], dev_in["B"], dev_in["C"], inp["D"], None, inp["bias"], dev_in["dout"], x, None, True)
+        res = [out] + [t for t in g if t is not None]
+        if host_out is None:
+            host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res]
+            d2h = sum(t.numel() * t.element_size() for t in res)
+        for h, t in zip(host_out, res):
+            h.copy_(t, non_blocking=True)
+
+    for _ in range(max(1, warmup)):
+        one()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), h2d, d2h
+
+
+def cpu_reference_run(w, steps, warmup, budget_s=150.0):
+    """The reference's own CPU algorithm (oracle/selective_scan_ref.py = restatement of selective_scan_ref +
+    torch autograd, all host threads) on a BOUNDED sample of the workload: one image (B=1), and if K steps of
+    that would not fit the time budget, a leading subset of the rows (rows are independent; the figure is
+    scaled by rows/R because a patch-token spans all R rows)."""
+    from oracle.selective_scan_ref import selective_scan_ref_fwd_bwd
+    R, G, L, N = w["R"], w["G"], w["L"], w["N"]
+    Ls = min(L, 196 * 2)   # the oracle's autograd backward is O(L^2): cap the sequence, tokens/s stays per token
+    g = torch.Generator().manual_seed(0)
+
+    def mk(rows):
+        rg = rows // G
+        A = -0.5 * torch.rand(rows, N, generator=g)
+        Bm = torch.randn(1, G, N, Ls, generator=g)
+        C = torch.randn(1, G, N, Ls, generator=g)
+        D = torch.randn(rows, generator=g)
+        bias = 0.5 * torch.rand(rows, generator=g)
+        u = torch.randn(1, rows, Ls, generator=g)
+        delta = 0.5 * torch.rand(1, rows, Ls, generator=g)
+        dout = torch.randn(1, rows, Ls, generator=g)
+        assert rg * G == rows
+        return (u, delta, A, Bm, C, D, None, bias, True, dout)
+
+    rows = R
+    probe_rows = min(R, 4 * G * 8)
+    probe = mk(probe_rows)
+    selective_scan_ref_fwd_bwd(*probe)                            # warms torch's thread pool up
+    t0 = time.perf_counter()
+    selective_scan_ref_fwd_bwd(*probe)
+    t_probe = time.perf_counter() - t0
+    est = t_probe * R / probe_rows
+    while rows > G * 8 and est * (steps + warmup) * rows / R > budget_s:
+        rows //= 2
+    args = mk(rows)
+    for _ in range(warmup):
+        selective_scan_ref_fwd_bwd(*args)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        selective_scan_ref_fwd_bwd(*args)
+    dt = time.perf_counter() - t0
+    value = steps * Ls * (rows / R) / dt
+    sample = f"B=1, L={Ls}, rows={rows}/{R} (value scaled by rows/R), d_state={N}, fp32, {steps} steps"
+    return value, dt * 1e3 / steps, sample, torch.get_num_threads()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    fwd_b, bwd_b = bytes_per_token(w)
+    config = {"workload": f"{args.workload}: selective scan fwd+bwd, B={w['B']}/GPU, R=3072 (K=4 x d_inner 768), G=4, L={w['L']}, "
+                          f"d_state={w['N']}, bf16 in, {'fp32' if w['out_f32'] else 'bf16'} out/dout",
+              "bytes_per_token": fwd_b + bwd_b, "l2": "working set > L2 (no flush needed)", "parallelism": f"dp{world}"}
+
+    if args.impl == "reference":
+        # the reference's CPU path (its selective_scan_ref) on the host cores; rank 0 only
+        if rank != 0:
+            return
+        steps = max(1, args.steps)
+        value, ms, sample, cores = cpu_reference_run(w, steps, min(args.warmup, 1))
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "patch-tokens/s", "n_gpus": args.gpus, "steps": steps,
+                "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": "patch-tokens/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": value, "unit": "patch-tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (use --impl reference for the CPU arm)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from medical_image_analysis_b200 import _lib
+
+    inp = make_inputs(w, dev, seed=rank)
+    dist_grads = None
+    if world > 1:
+        def dist_grads(g):  # DDP's gradient step: all-reduce of the parameter gradients only
+            flat = torch.cat([g[2].flatten(), g[5], g[6]])
+            dist.all_reduce(flat)
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    # warm-up happens inside; the sampler runs across the timed steps
+    launches0 = None
+    from medical_image_analysis_b200 import scan_bwd, scan_fwd  # noqa: F401
+    sampler.start()
+    # a short sustained pre-roll so nvidia-smi sees load, then the measured region
+    run_device_steps(inp, max(3, args.warmup), 0, dist_grads)
+    launches0 = _lib.launch_count()
+    total_ms, fwd_ms, bwd_ms = run_device_steps(inp, args.steps, 0, dist_grads)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop()
+    t = torch.tensor([total_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    tokens_per_step = w["B"] * w["L"] * world
+    value = tokens_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end: host buffers in, host buffers out
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_ms, h2d, d2h = run_e2e_steps(w, inp, e2e_steps, 2)
+    t = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = tokens_per_step * e2e_steps / (float(t.item()) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    per_gpu_tokens = w["B"] * w["L"]
+    bwd_gbs = per_gpu_tokens * bwd_b / (bwd_ms * 1e-3) / 1e9
+    fwd_gbs = per_gpu_tokens * fwd_b / (fwd_ms * 1e-3) / 1e9
+    step_gbs = (value / world) * (fwd_b + bwd_b) / 1e9
+    roofline = {"bound": "hbm", "kernel": "ss_bwd_kernel<bf16> (+ss_finalize_kernel, timed together as the bwd C-ABI call)",
+                "achieved": bwd_gbs, "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": per_gpu_tokens * bwd_b,
+                "fwd_kernel": {"achieved": fwd_gbs, "frac": fwd_gbs / peak, "algorithmic_bytes_per_launch": per_gpu_tokens * fwd_b},
+                "step": {"achieved": step_gbs, "frac": step_gbs / peak, "roofline_tokens_per_s": peak * 1e9 / (fwd_b + bwd_b)}}
+    line = {"metric": METRIC, "value": value, "unit": "patch-tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "patch-tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "roofline": roofline}
+    line["config"]["compute"] = "fp32 scan arithmetic on bf16 activations (dtype key = arithmetic type)"
+
+    if not args.no_extras and world == 1:
+        extras = []
+        for name, ww in WORKLOADS.items():
+            if name == args.workload:
+                continue
+            try:
+                i2 = make_inputs(ww, dev, seed=1)
+                run_device_steps(i2, 3, 0)
+                tms, f_ms, b_ms = run_device_steps(i2, 10, 0)
+                fb, bb = bytes_per_token(ww)
+                v = ww["B"] * ww["L"] * 10 / (tms * 1e-3)
+                extras.append({"workload": name, "B": ww["B"], "value": v, "ms_per_step": tms / 10, "fwd_ms": f_ms, "bwd_ms": b_ms,
+                               "bytes_per_token": fb + bb, "hbm_frac": v * (fb + bb) / 1e9 / peak})
+                del i2
+                torch.cuda.empty_cache()
+            except Exception as e:  # report, never hide
+                extras.append({"workload": name, "error": repr(e)})
+        line["extra_workloads"] = extras
+
+    if not args.no_cpu:
+        cv, cms, sample, cores = cpu_reference_run(w, 2, 0, budget_s=20.0)
+        line["cpu_baseline"] = {"value": cv, "unit": "patch-tokens/s", "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
