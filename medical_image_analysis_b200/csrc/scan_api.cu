@@ -63,10 +63,18 @@ struct WorkspaceLayout {
     bool bc_atomic = false;
 };
 
-// Tile plan shared by fwd and bwd (the checkpoint geometry must match between them).
+// Work plan shared by fwd and bwd (the checkpoint geometry must match between them).
 struct Plan {
-    int LPR, CH, n_chunks, RPP, NW, RT, tiles_per_group, n_items;
+    int LPR, CH, n_chunks, RPP, NW, RT, RS, split, tiles_per_seg, n_seg;
 };
+
+void set_split(Plan &pl, const mia_ss_params &p, int split) {
+    const int rpg = p.dim / p.n_groups;
+    pl.RS = (rpg + split - 1) / split;
+    pl.split = (rpg + pl.RS - 1) / pl.RS;
+    pl.tiles_per_seg = (pl.RS + pl.RT - 1) / pl.RT;
+    pl.n_seg = p.batch * p.n_groups * pl.split;
+}
 
 Plan make_plan(const mia_ss_params &p, int sms) {
     Plan pl;
@@ -74,30 +82,40 @@ Plan make_plan(const mia_ss_params &p, int sms) {
     pl.CH = pl.LPR * mia::kTok;
     pl.n_chunks = (p.seqlen + pl.CH - 1) / pl.CH;
     pl.RPP = 32 / pl.LPR;
-    pl.NW = 15;  // + 1 producer warp = 512 threads: 4 warps per SM sub-partition, 128 registers each
-    const int rows_per_group = p.dim / p.n_groups;
-    int rows_per_warp = 2;
-    int RT = pl.NW * pl.RPP * rows_per_warp;
-    // enough items to balance the persistent grid; never more rows than the group has; bound carry arrays
-    auto items = [&](int rt) { return (long long)p.batch * p.n_groups * ((rows_per_group + rt - 1) / rt); };
-    while (RT > pl.RPP && (items(RT) < 4LL * sms || RT * p.dstate > 8192)) RT >>= 1;
-    if (RT > rows_per_group) RT = round_up(rows_per_group, pl.RPP);
-    if (RT < 1) RT = 1;
-    pl.RT = RT;
-    pl.tiles_per_group = (rows_per_group + RT - 1) / RT;
-    pl.n_items = p.batch * p.n_groups * pl.tiles_per_group;
+    pl.NW = mia::kThreads / 32 - 1;
+    pl.RT = pl.NW * pl.RPP * 4;   // four row passes per warp and row stage (amortises the per-stage bookkeeping)
+    const int rpg = p.dim / p.n_groups;
+    // Segments: (batch, group, row range).  Aim at >= ~6 segments per SM with the best last-wave balance; a segment
+    // keeps its carries in shared memory, so bound rows * d_state.
+    const long long bg = (long long)p.batch * p.n_groups;
+    int max_split = (rpg + pl.RPP - 1) / pl.RPP;
+    int min_split = 1;
+    while ((long long)((rpg + min_split - 1) / min_split) * p.dstate > 4096 && min_split < max_split) ++min_split;
+    int want = (int)((6LL * sms + bg - 1) / bg);
+    if (want < min_split) want = min_split;
+    if (want > max_split) want = max_split;
+    int best = want;
+    double best_eff = -1.0;
+    for (int sp = want; sp <= want + 3 && sp <= max_split; ++sp) {
+        Plan t = pl;
+        set_split(t, p, sp);
+        const double waves = (double)t.n_seg / sms;
+        const double eff = waves / (double)((t.n_seg + sms - 1) / sms);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = sp; }
+    }
+    set_split(pl, p, best);
     return pl;
 }
 
 WorkspaceLayout workspace_layout(const mia_ss_params &p, const Plan &pl) {
     WorkspaceLayout w;
     auto take = [&](size_t nfloat) { size_t off = w.total; w.total += (nfloat * 4 + 255) / 256 * 256; return off; };
-    w.bc_atomic = p.dstate > 2;
+    w.bc_atomic = p.dstate > 1;
     w.part_dA = take((size_t)p.batch * p.dim * p.dstate);
     w.part_dD = take((size_t)p.batch * p.dim);
     w.part_dbias = take((size_t)p.batch * p.dim);
     size_t nacc = w.bc_atomic ? (size_t)p.batch * p.n_groups * p.dstate * ((p.seqlen + 3) & ~3)
-                              : (size_t)pl.n_items * p.dstate * p.seqlen;
+                              : (size_t)pl.n_seg * p.dstate * p.seqlen;
     w.acc_dB = take(nacc);
     w.acc_dC = take(nacc);
     w.acc_bytes = nacc * 4;
@@ -125,8 +143,8 @@ void fill_common(mia::ScanArgs &a, const mia_ss_params &p, const Plan &pl, bool 
     a.rows_per_group = p.dim / p.n_groups;
     a.delta_ratio = p.dim / p.delta_dim;
     a.softplus = p.delta_softplus; a.has_z = p.z != nullptr; a.out_f32 = (p.otype == MIA_F32) && (p.itype != MIA_F32);
-    a.RT = pl.RT; a.tiles_per_group = pl.tiles_per_group; a.LPR = pl.LPR; a.CH = pl.CH; a.n_chunks = pl.n_chunks;
-    a.n_items = pl.n_items; a.n_consumer_warps = pl.NW;
+    a.RT = pl.RT; a.RS = pl.RS; a.split = pl.split; a.tiles_per_seg = pl.tiles_per_seg; a.LPR = pl.LPR; a.CH = pl.CH;
+    a.n_chunks = pl.n_chunks; a.n_seg = pl.n_seg; a.n_consumer_warps = pl.NW;
     a.u = p.u; a.delta = p.delta; a.A = p.A; a.B = p.B; a.C = p.C; a.D = p.D; a.delta_bias = p.delta_bias; a.z = p.z;
     a.x = p.x;
     a.u_bs = p.u_batch_stride; a.u_ds = p.u_d_stride; a.delta_bs = p.delta_batch_stride; a.delta_ds = p.delta_d_stride;
@@ -142,13 +160,13 @@ void fill_common(mia::ScanArgs &a, const mia_ss_params &p, const Plan &pl, bool 
     (void)bwd;
 }
 
-// Shared-memory carve-up.  Returns false if not even two stages fit.
+// Shared-memory carve-up.  Returns false if not even two row stages fit.
 bool layout_smem(mia::ScanArgs &a, int es, int eso, bool bwd, int smem_max) {
     const int span = a.CH < a.L ? a.CH : a.L;
     a.row_pitch = round_up(span * es, 16) + 16;
     a.rowo_pitch = round_up(span * eso, 16) + 16;
     a.bc_pitch = a.row_pitch;
-    const int slack = a.CH * 4 + 16;
+    const int slack = a.CH * 4 + 16;   // an 8-token vector read may run past the last row of a region
     int off = 0;
     auto region = [&](int rows, int pitch) { int o = off; off += round_up(rows * pitch + slack, 128); return o; };
     a.off_u = region(a.RT, a.row_pitch);
@@ -157,31 +175,38 @@ bool layout_smem(mia::ScanArgs &a, int es, int eso, bool bwd, int smem_max) {
     if (bwd) {
         a.off_dout = region(a.RT, a.rowo_pitch);
         if (a.has_z) a.off_osaved = region(a.RT, a.rowo_pitch);
+        a.off_h0 = off; off += round_up(a.RT * a.N * 4, 128);
     }
-    a.off_B = region(a.N, a.bc_pitch);
-    a.off_C = region(a.N, a.bc_pitch);
     a.stage_bytes = off;
-    int fixed = 0;
-    const int bars = 2 * mia::kMaxStages * 8;
-    int carry = bwd ? (2 * a.RT * a.N + 2 * a.RT) * 4 : a.RT * a.N * 8;
-    carry = round_up(carry, 128);
+    off = 0;
+    a.goff_B = region(a.N, a.bc_pitch);
+    a.goff_C = region(a.N, a.bc_pitch);
+    a.goff_A = off; off += round_up(a.RS * a.N * 4, 128);
+    a.goff_D = off; off += round_up(a.RS * 4, 128);
+    a.goff_bias = off; off += round_up(a.RS * 4, 128);
+    a.gstage_bytes = off;
+    const int bars = round_up((2 * mia::kMaxStages + 2 * mia::kGroupStages) * 8, 128);
+    const int carry = round_up(bwd ? (2 * a.RS * a.N + 2 * a.RS) * 4 : a.RS * a.N * 8, 128);
     const int red = bwd ? a.n_consumer_warps * 256 * 4 : 0;
-    fixed = round_up(bars, 128) + carry + red;
+    const int fixed = mia::kGroupStages * a.gstage_bytes + bars + carry + red;
     int stages = (smem_max - fixed) / a.stage_bytes;
     if (stages > mia::kMaxStages) stages = mia::kMaxStages;
     if (stages < 2) return false;
     a.stages = stages;
-    a.off_bars = stages * a.stage_bytes;
-    a.off_carry = a.off_bars + round_up(bars, 128);
+    a.off_groups = stages * a.stage_bytes;
+    a.off_bars = a.off_groups + mia::kGroupStages * a.gstage_bytes;
+    a.off_carry = a.off_bars + bars;
     a.off_red = a.off_carry + carry;
     a.smem_bytes = a.off_red + red;
     return true;
 }
 
-// Pick the tile plan and carve shared memory; halves the row tile until at least two stages fit.
+// Pick the work plan and carve shared memory; if it does not fit, first cut segments finer (smaller carries and
+// parameter blocks), then halve the row tile.
 int plan_and_layout(const mia_ss_params &p, const DeviceInfo &di, bool bwd, Plan &pl, mia::ScanArgs &a) {
     pl = make_plan(p, di.sms);
     const int es = esize(p.itype), eso = esize(p.otype);
+    const int rpg = p.dim / p.n_groups;
     for (;;) {
         fill_common(a, p, pl, bwd);
         if (bwd) {
@@ -190,10 +215,13 @@ int plan_and_layout(const mia_ss_params &p, const DeviceInfo &di, bool bwd, Plan
             a.flat_osaved = a.has_z && whole && p.out_saved_d_stride == p.seqlen;
         }
         if (layout_smem(a, es, eso, bwd, di.smem_optin)) return MIA_OK;
-        MIA_CHECK(pl.RT > pl.RPP, "tile does not fit in shared memory (dstate %d, seqlen %d)", p.dstate, p.seqlen);
-        pl.RT = pl.RT / 2 < pl.RPP ? pl.RPP : pl.RT / 2;
-        pl.tiles_per_group = (p.dim / p.n_groups + pl.RT - 1) / pl.RT;
-        pl.n_items = p.batch * p.n_groups * pl.tiles_per_group;
+        if (pl.RS > pl.RT) {
+            set_split(pl, p, pl.split * 2 < rpg ? pl.split * 2 : rpg);
+        } else {
+            MIA_CHECK(pl.RT > pl.RPP, "tile does not fit in shared memory (dstate %d, seqlen %d)", p.dstate, p.seqlen);
+            pl.RT = pl.RT / 2 < pl.RPP ? pl.RPP : pl.RT / 2;
+            set_split(pl, p, pl.split);
+        }
     }
 }
 
@@ -217,65 +245,76 @@ struct FinArgs {
     long long n_bc, n_dA, n_dD, n_db, n_dd;
 };
 
+// thread items: dB, dC (sum of the per-segment partials / cast of the atomic accumulator) and the ddelta group fold;
+// warp items: dA, dD, dbias (sum over the batch, lanes stride over b, shuffle-reduced in a fixed order).
 template <typename T>
 __global__ void ss_finalize_kernel(const __grid_constant__ FinArgs f) {
     using raw = typename mia::Cvt<T>::raw;
-    const long long total = 2 * f.n_bc + f.n_dA + f.n_dD + f.n_db + f.n_dd;
+    const long long n_thread_items = 2 * f.n_bc + f.n_dd;
+    const long long t1 = (n_thread_items + 31) / 32 * 32;
+    const long long n_warp_items = f.n_dA + f.n_dD + f.n_db;
+    const long long total = t1 + 32 * n_warp_items;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        long long i = idx;
-        if (i < 2 * f.n_bc) {
-            const bool isC = i >= f.n_bc;
-            if (isC) i -= f.n_bc;
-            const int l = (int)(i % f.L);
-            long long t = i / f.L;
-            const int n = (int)(t % f.N); t /= f.N;
-            const int g = (int)(t % f.G);
-            const int b = (int)(t / f.G);
-            const float *acc = isC ? f.acc_dC : f.acc_dB;
-            float sum = 0.f;
-            if (f.bc_atomic) {
-                sum = acc[((size_t)(b * f.G + g) * f.N + n) * f.Lp + l];
-            } else {
-                for (int tl = 0; tl < f.tiles; ++tl) sum += acc[(((size_t)(b * f.G + g) * f.tiles + tl) * f.N + n) * f.L + l];
+        if (idx < t1) {
+            long long i = idx;
+            if (i >= n_thread_items) continue;
+            if (i < 2 * f.n_bc) {
+                const bool isC = i >= f.n_bc;
+                if (isC) i -= f.n_bc;
+                const int l = (int)(i % f.L);
+                long long t = i / f.L;
+                const int n = (int)(t % f.N); t /= f.N;
+                const int g = (int)(t % f.G);
+                const int b = (int)(t / f.G);
+                const float *acc = isC ? f.acc_dC : f.acc_dB;
+                float sum = 0.f;
+                if (f.bc_atomic) {
+                    sum = acc[((size_t)(b * f.G + g) * f.N + n) * f.Lp + l];
+                } else {
+                    const float *p0 = acc + (((size_t)(b * f.G + g) * f.tiles) * f.N + n) * f.L + l;
+                    const size_t step = (size_t)f.N * f.L;
+#pragma unroll 4
+                    for (int tl = 0; tl < f.tiles; ++tl) sum += p0[tl * step];
+                }
+                raw *dst = reinterpret_cast<raw *>(isC ? f.dC : f.dB);
+                const long long o = isC ? (b * f.dC_bs + g * f.dC_gs + n * f.dC_ns + l) : (b * f.dB_bs + g * f.dB_gs + n * f.dB_ns + l);
+                dst[o] = mia::Cvt<T>::from_f(sum);
+            } else {   // ddelta fold over the delta group (selective_scan_oflex.cpp:348-350)
+                i -= 2 * f.n_bc;
+                const int l = (int)(i % f.L);
+                long long t = i / f.L;
+                const int dg = (int)(t % f.delta_dim);
+                const int b = (int)(t / f.delta_dim);
+                float sum = 0.f;
+                for (int r = 0; r < f.ratio; ++r) sum += f.ddelta_full[((size_t)b * f.dim + dg * f.ratio + r) * f.L + l];
+                reinterpret_cast<raw *>(f.ddelta)[b * f.dd_bs + dg * f.dd_ds + l] = mia::Cvt<T>::from_f(sum);
             }
-            raw *dst = reinterpret_cast<raw *>(isC ? f.dC : f.dB);
-            const long long o = isC ? (b * f.dC_bs + g * f.dC_gs + n * f.dC_ns + l) : (b * f.dB_bs + g * f.dB_gs + n * f.dB_ns + l);
-            dst[o] = mia::Cvt<T>::from_f(sum);
             continue;
         }
-        i -= 2 * f.n_bc;
-        if (i < f.n_dA) {
-            const int n = (int)(i % f.N), d = (int)(i / f.N);
-            float sum = 0.f;
-            for (int b = 0; b < f.batch; ++b) sum += f.part_dA[((size_t)b * f.dim + d) * f.N + n];
-            f.dA[d * f.dA_ds + n * f.dA_ns] = sum;
-            continue;
+        // ---- warp items (idx - t1 is warp aligned, so the whole warp takes this path together)
+        long long w = (idx - t1) >> 5;
+        const int lane = (int)(idx & 31);
+        float sum = 0.f;
+        float *dst;
+        if (w < f.n_dA) {
+            const int n = (int)(w % f.N), d = (int)(w / f.N);
+            for (int b = lane; b < f.batch; b += 32) sum += f.part_dA[((size_t)b * f.dim + d) * f.N + n];
+            dst = f.dA + d * f.dA_ds + n * f.dA_ns;
+        } else if (w < f.n_dA + f.n_dD) {
+            w -= f.n_dA;
+            for (int b = lane; b < f.batch; b += 32) sum += f.part_dD[(size_t)b * f.dim + w];
+            dst = f.dD + w;
+        } else {
+            w -= f.n_dA + f.n_dD;
+            for (int k = lane; k < f.batch * f.ratio; k += 32) {
+                const int b = k / f.ratio, r = k - b * f.ratio;
+                sum += f.part_dbias[(size_t)b * f.dim + w * f.ratio + r];
+            }
+            dst = f.dbias + w;
         }
-        i -= f.n_dA;
-        if (i < f.n_dD) {
-            float sum = 0.f;
-            for (int b = 0; b < f.batch; ++b) sum += f.part_dD[(size_t)b * f.dim + i];
-            f.dD[i] = sum;
-            continue;
-        }
-        i -= f.n_dD;
-        if (i < f.n_db) {
-            float sum = 0.f;
-            for (int b = 0; b < f.batch; ++b)
-                for (int r = 0; r < f.ratio; ++r) sum += f.part_dbias[(size_t)b * f.dim + i * f.ratio + r];
-            f.dbias[i] = sum;
-            continue;
-        }
-        i -= f.n_db;
-        {   // ddelta fold over the delta group (selective_scan_oflex.cpp:348-350)
-            const int l = (int)(i % f.L);
-            long long t = i / f.L;
-            const int dg = (int)(t % f.delta_dim);
-            const int b = (int)(t / f.delta_dim);
-            float sum = 0.f;
-            for (int r = 0; r < f.ratio; ++r) sum += f.ddelta_full[((size_t)b * f.dim + dg * f.ratio + r) * f.L + l];
-            reinterpret_cast<raw *>(f.ddelta)[b * f.dd_bs + dg * f.dd_ds + l] = mia::Cvt<T>::from_f(sum);
-        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        if (lane == 0) *dst = sum;
     }
 }
 
@@ -307,7 +346,7 @@ int mia_selective_scan_fwd(const mia_ss_params *pp, void *cuda_stream) {
     if (int rc = plan_and_layout(p, di, false, pl, a)) return rc;
     a.out = p.out; a.out_z = p.out_z;
     a.out_bs = p.out_batch_stride; a.out_ds = p.out_d_stride; a.outz_bs = p.out_z_batch_stride; a.outz_ds = p.out_z_d_stride;
-    const int grid = a.n_items < di.sms ? a.n_items : di.sms;
+    const int grid = a.n_seg < di.sms ? a.n_seg : di.sms;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     const int rc = dispatch(p.itype, [&](auto *tag) {
         using T = typename std::remove_pointer<decltype(tag)>::type;
@@ -362,7 +401,7 @@ int mia_selective_scan_bwd(const mia_ss_params *pp, void *cuda_stream) {
         MIA_CUDA(cudaMemsetAsync(a.acc_dC, 0, w.acc_bytes, stream));
         g_launches.fetch_add(2);
     }
-    const int grid = a.n_items < di.sms ? a.n_items : di.sms;
+    const int grid = a.n_seg < di.sms ? a.n_seg : di.sms;
     int rc = dispatch(p.itype, [&](auto *tag) {
         using T = typename std::remove_pointer<decltype(tag)>::type;
         return (int)mia::launch_bwd<T>(a, grid, stream);
@@ -373,7 +412,7 @@ int mia_selective_scan_bwd(const mia_ss_params *pp, void *cuda_stream) {
     FinArgs f;
     memset(&f, 0, sizeof(f));
     f.batch = p.batch; f.dim = p.dim; f.L = p.seqlen; f.N = p.dstate; f.G = p.n_groups; f.delta_dim = p.delta_dim;
-    f.ratio = p.dim / p.delta_dim; f.tiles = pl.tiles_per_group; f.bc_atomic = w.bc_atomic; f.Lp = (p.seqlen + 3) & ~3;
+    f.ratio = p.dim / p.delta_dim; f.tiles = pl.split; f.bc_atomic = w.bc_atomic; f.Lp = (p.seqlen + 3) & ~3;
     f.part_dA = a.part_dA; f.part_dD = a.part_dD; f.part_dbias = a.part_dbias; f.acc_dB = a.acc_dB; f.acc_dC = a.acc_dC;
     f.ddelta_full = a.ddelta_full;
     f.dA = p.dA; f.dD = p.dD; f.dbias = p.ddelta_bias; f.dB = p.dB; f.dC = p.dC; f.ddelta = p.ddelta;
@@ -386,7 +425,7 @@ int mia_selective_scan_bwd(const mia_ss_params *pp, void *cuda_stream) {
     f.n_dD = p.D ? p.dim : 0;
     f.n_db = p.delta_bias ? p.delta_dim : 0;
     f.n_dd = f.ratio > 1 ? (long long)p.batch * p.delta_dim * p.seqlen : 0;
-    const long long total = 2 * f.n_bc + f.n_dA + f.n_dD + f.n_db + f.n_dd;
+    const long long total = (2 * f.n_bc + f.n_dd + 31) / 32 * 32 + 32 * (f.n_dA + f.n_dD + f.n_db);
     long long blocks = (total + 255) / 256;
     if (blocks > di.sms * 8) blocks = di.sms * 8;
     rc = dispatch(p.itype, [&](auto *tag) {

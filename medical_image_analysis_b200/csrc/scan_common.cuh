@@ -1,11 +1,14 @@
 // Device-side building blocks shared by the forward and backward selective-scan kernels (sm_100a).
 //
-// Design: persistent CTAs; one producer warp stages (u, delta, [z, dout, out], B, C)
-// tiles into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx) through a
-// multi-stage full/empty ring; consumer warps own rows.  A row chunk is LPR lanes x 8 consecutive tokens:
-// every lane scans its 8 tokens serially in registers, the lane aggregates are combined with a
-// warp-shuffle scan of (a, b) pairs under the operator (a, b) o (a', b') = (a a', a' b + b')
-// (the algebra of selective_scan_common.h:91-96 in the reference), chunks are chained through a carry.
+// Design.  Persistent CTAs of 15 consumer warps + 1 producer warp.  Work is cut into SEGMENTS
+// (batch b, B/C group g, a contiguous range of the group's rows).  For every (segment, chunk of <= 256 tokens)
+// the producer stages one GROUP stage (the B and C chunk for all d_state rows + the per-row parameters
+// A*log2e, D, delta_bias) and then streams the segment's rows through a ring of ROW stages (u, delta,
+// [z, dout, out, h0]) -- all with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx), full/empty
+// mbarrier pairs, no block-wide barrier in the steady state.  Consumer warps own rows: a row chunk is LPR lanes x
+// 8 consecutive tokens, every lane scans its 8 tokens serially in registers, the lane aggregates are combined by
+// a warp-shuffle scan of (a, b) pairs under (a, b) o (a', b') = (a a', a' b + b') (the algebra of
+// selective_scan_common.h:91-96 in the reference), chunks are chained through shared-memory carries.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -18,6 +21,8 @@ constexpr int kTok = 8;  // tokens per lane per chunk
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr int kMaxStages = 8;
+constexpr int kGroupStages = 2;
+constexpr int kThreads = 512;  // 15 consumer warps + 1 producer: 4 warps per SM sub-partition, 128 registers each
 
 // ------------------------------------------------------------------------------------------------
 // Kernel argument block (built on the host by scan_api.cu).
@@ -27,13 +32,14 @@ struct ScanArgs {
     int rows_per_group, delta_ratio;
     int softplus, has_z, out_f32;      // out_f32: dtype of out/out_z (fwd) or dout/out_saved (bwd) is float
     // tiling
-    int RT, tiles_per_group, LPR, CH, n_chunks, n_items, stages, n_consumer_warps;
-    // span-merge flags (whole tile is one contiguous span in global memory)
+    int RT, RS, split, tiles_per_seg, LPR, CH, n_chunks, n_seg, stages, n_consumer_warps;
+    // span-merge flags (the rows of a tile are back to back in global memory -> one TMA span)
     int flat_u, flat_delta, flat_z, flat_dout, flat_osaved, flat_B, flat_C;
     // shared-memory layout (bytes)
     int row_pitch, rowo_pitch, bc_pitch;
-    int off_u, off_delta, off_z, off_dout, off_osaved, off_B, off_C, stage_bytes;
-    int off_bars, off_carry, off_red, smem_bytes;
+    int off_u, off_delta, off_z, off_dout, off_osaved, off_h0, stage_bytes;   // inside a row stage
+    int goff_B, goff_C, goff_A, goff_D, goff_bias, gstage_bytes;              // inside a group stage
+    int off_groups, off_bars, off_carry, off_red, smem_bytes;                 // row stages start at 0
     // pointers
     const void *u, *delta, *A, *B, *C, *D, *delta_bias, *z;
     void *out, *out_z;
@@ -41,7 +47,7 @@ struct ScanArgs {
     const void *dout, *out_saved;
     void *du, *ddelta, *dz;
     float *part_dA, *part_dD, *part_dbias;   // (batch, dim, N) / (batch, dim) / (batch, dim) f32 partials
-    float *acc_dB, *acc_dC;                  // N <= 2: (batch*G*tiles, N, L) partials ; else (batch, G, N, L) atomics
+    float *acc_dB, *acc_dC;                  // N <= 2: (n_seg, N, L) partials ; else (batch, G, N, Lp) atomics
     float *ddelta_full;                      // (batch, dim, L) f32 when delta_ratio > 1
     int bc_atomic;
     // strides (elements)
@@ -60,6 +66,7 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -88,17 +95,16 @@ __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f3
 __device__ __forceinline__ float lg2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcpf(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// softplus with the reference's threshold (fwd_kernel_oflex.cuh:126: x <= 20 ? log1p(exp(x)) : x) plus, optionally, its
-// derivative sigmoid(x) (bwd_kernel_oflex.cuh:252-257).  log1p is evaluated by a series for small e so that the usual
-// Mamba range (dt ~ 1e-3..1e-1) keeps full relative precision without the libm log1pf.
+// softplus(x) = log1p(exp(x)) for x <= 20, x above (fwd_kernel_oflex.cuh:126), and optionally its derivative
+// sigmoid(x) (bwd_kernel_oflex.cuh:252-257).  Evaluated as max(lg2(1 + 2^min(x log2e, 120)) ln2, x): for 20 < x the
+// log1p term equals x to fp32 precision, the clamp keeps 2^. finite, the max restores x where the clamp bit.
+// Absolute error <= 1 ulp of 1.0 (6e-8), which is what enters exp(dl A) and dl u B.
 template <bool kWithSigmoid>
 __device__ __forceinline__ float softplus_f(float x, float &sig) {
-    const float e = ex2f(x * kLog2e);
+    const float e = ex2f(fminf(x * kLog2e, 120.f));
     const float s = 1.f + e;
-    const float series = e * (1.f + e * (-0.5f + e * (0.33333334f + e * (-0.25f + e * 0.2f))));
-    float sp = e < 0.06f ? series : lg2f(s) * kLn2;
-    if (kWithSigmoid) sig = x <= 20.f ? e * rcpf(s) : 1.f;
-    return x <= 20.f ? sp : x;
+    if (kWithSigmoid) sig = e * rcpf(s);
+    return fmaxf(lg2f(s) * kLn2, x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -123,33 +129,40 @@ template <> struct Cvt<__nv_bfloat16> {
 
 template <typename T> struct Pack8 { typename Cvt<T>::raw v[kTok]; };
 
-// load 8 consecutive T from (possibly only element-aligned) address p (shared or global) into floats
+// 8 consecutive T from a SHARED-memory address (32-bit shared-window address, element aligned) -> floats
 template <typename T>
-__device__ __forceinline__ void ld8(const void *p, float (&f)[kTok]) {
+__device__ __forceinline__ void lds8(uint32_t saddr, float (&f)[kTok]) {
     constexpr int kBytes = kTok * (int)sizeof(T);
     union { Pack8<T> t; uint4 q[kBytes / 16]; uint2 d[kBytes / 8]; uint32_t w[kBytes / 4]; } buf;
-    const uintptr_t a = (uintptr_t)p;
-    if ((a & 15) == 0) {
+    if ((saddr & 15) == 0) {
 #pragma unroll
-        for (int i = 0; i < kBytes / 16; ++i) buf.q[i] = reinterpret_cast<const uint4 *>(p)[i];
-    } else if ((a & 7) == 0) {
+        for (int i = 0; i < kBytes / 16; ++i)
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(buf.q[i].x), "=r"(buf.q[i].y), "=r"(buf.q[i].z), "=r"(buf.q[i].w)
+                         : "r"(saddr + 16 * i));
+    } else if ((saddr & 7) == 0) {
 #pragma unroll
-        for (int i = 0; i < kBytes / 8; ++i) buf.d[i] = reinterpret_cast<const uint2 *>(p)[i];
-    } else if ((a & 3) == 0) {
+        for (int i = 0; i < kBytes / 8; ++i)
+            asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(buf.d[i].x), "=r"(buf.d[i].y) : "r"(saddr + 8 * i));
+    } else if ((saddr & 3) == 0) {
 #pragma unroll
-        for (int i = 0; i < kBytes / 4; ++i) buf.w[i] = reinterpret_cast<const uint32_t *>(p)[i];
+        for (int i = 0; i < kBytes / 4; ++i) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(buf.w[i]) : "r"(saddr + 4 * i));
     } else {
 #pragma unroll
-        for (int i = 0; i < kTok; ++i) buf.t.v[i] = reinterpret_cast<const typename Cvt<T>::raw *>(p)[i];
+        for (int i = 0; i < kTok; ++i) {
+            uint16_t h;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(saddr + 2 * i));
+            buf.t.v[i] = (typename Cvt<T>::raw)h;
+        }
     }
 #pragma unroll
     for (int i = 0; i < kTok; ++i) f[i] = Cvt<T>::to_f(buf.t.v[i]);
 }
 
-// store up to 8 consecutive T to global memory (nvalid may be < 8 at the sequence tail)
+// store up to 8 consecutive T to global memory (nvalid < 8 only in the lane that holds the sequence tail)
 template <typename T>
 __device__ __forceinline__ void st8(void *p, const float (&f)[kTok], int nvalid) {
     constexpr int kBytes = kTok * (int)sizeof(T);
+    constexpr int kPer4 = 4 / (int)sizeof(T);       // elements per 32-bit word
     union { Pack8<T> t; uint4 q[kBytes / 16]; uint2 d[kBytes / 8]; uint32_t w[kBytes / 4]; } buf;
 #pragma unroll
     for (int i = 0; i < kTok; ++i) buf.t.v[i] = Cvt<T>::from_f(f[i]);
@@ -163,11 +176,14 @@ __device__ __forceinline__ void st8(void *p, const float (&f)[kTok], int nvalid)
 #pragma unroll
             for (int i = 0; i < kBytes / 8; ++i) reinterpret_cast<uint2 *>(p)[i] = buf.d[i];
             return;
-        } else if ((a & 3) == 0) {
-#pragma unroll
-            for (int i = 0; i < kBytes / 4; ++i) reinterpret_cast<uint32_t *>(p)[i] = buf.w[i];
-            return;
         }
+    }
+    if ((a & 3) == 0) {   // word stores for the full words, then at most one trailing element
+#pragma unroll
+        for (int i = 0; i < kBytes / 4; ++i)
+            if ((i + 1) * kPer4 <= nvalid) reinterpret_cast<uint32_t *>(p)[i] = buf.w[i];
+        if (kPer4 == 2 && (nvalid & 1)) reinterpret_cast<typename Cvt<T>::raw *>(p)[nvalid - 1] = buf.t.v[(nvalid - 1) & 7];
+        return;
     }
 #pragma unroll
     for (int i = 0; i < kTok; ++i)
@@ -212,64 +228,131 @@ __device__ __forceinline__ uint32_t stage_rows(char *region, const char *g0, lon
     return tx;
 }
 
-// Consumer side: shared-memory address of element 0 of row chunk r inside a region staged by stage_rows.
-__device__ __forceinline__ const char *staged_row(const char *region, const char *g0, long long row_stride, int r, int len, int es,
-                                                  int pitch, bool flat) {
-    if (flat) return region + ((uintptr_t)g0 & 15u) + (size_t)r * len * es;
-    const char *grow = g0 + (size_t)r * row_stride * es;
-    return region + (size_t)r * pitch + ((uintptr_t)grow & 15u);
+// Consumer side view of a region staged by stage_rows: row r starts at base + r * pitch + ((g0lo + r * gstep) & 15).
+// (flat: pitch = len * es, gstep = 0, so the misalignment is that of the tile start.)
+struct RowView {
+    uint32_t base, pitch, g0lo, gstep;
+    __device__ __forceinline__ uint32_t row(int r) const { return base + r * pitch + ((g0lo + r * gstep) & 15u); }
+};
+__device__ __forceinline__ RowView make_view(const char *region, const char *g0, long long row_stride, int len, int es, int pitch,
+                                             bool flat) {
+    RowView v;
+    v.base = smem_u32(region);
+    v.g0lo = (uint32_t)(uintptr_t)g0;
+    if (flat) { v.pitch = (uint32_t)(len * es); v.gstep = 0; }
+    else { v.pitch = (uint32_t)pitch; v.gstep = (uint32_t)(row_stride * es); }
+    return v;
 }
 
-struct ItemCoord { int b, g, tile, row0, nrows; };
-__device__ __forceinline__ ItemCoord decode_item(const ScanArgs &a, int item) {
-    ItemCoord c;
-    c.tile = item % a.tiles_per_group;
-    const int bg = item / a.tiles_per_group;
+struct SegCoord { int b, g, row_lo, nrows; };
+__device__ __forceinline__ SegCoord decode_seg(const ScanArgs &a, int seg) {
+    SegCoord c;
+    const int s = seg % a.split;
+    const int bg = seg / a.split;
     c.g = bg % a.G;
     c.b = bg / a.G;
-    const int in_group = c.tile * a.RT;
-    c.row0 = c.g * a.rows_per_group + in_group;
-    c.nrows = min(a.RT, a.rows_per_group - in_group);
+    const int in_group = s * a.RS;
+    c.row_lo = c.g * a.rows_per_group + in_group;
+    c.nrows = min(a.RS, a.rows_per_group - in_group);
     return c;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Warp-shuffle scans of (a, b) pairs over segments of `lpr` lanes (lpr is a power of two, j = lane % lpr).
+// kLPR == 32: the row is the whole warp, everything unrolls without width bookkeeping; kLPR == 0: runtime lpr.
 // Forward: on return (pa, pb) is the inclusive aggregate of lanes [0..j]; (ea, eb) the exclusive one.
+template <int kLPR>
 __device__ __forceinline__ void seg_scan_fwd(float &pa, float &pb, float &ea, float &eb, int j, int lpr) {
-    for (int off = 1; off < lpr; off <<= 1) {
-        float qa = __shfl_up_sync(0xffffffffu, pa, off, lpr);
-        float qb = __shfl_up_sync(0xffffffffu, pb, off, lpr);
-        const bool ok = j >= off;
-        qa = ok ? qa : 1.f;
-        qb = ok ? qb : 0.f;
-        pb = fmaf(pa, qb, pb);   // earlier segment (qa,qb) then ours (pa,pb): (qa pa, pa qb + pb)
-        pa = pa * qa;
+    if (kLPR == 32) {
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            float qa = __shfl_up_sync(0xffffffffu, pa, off);
+            float qb = __shfl_up_sync(0xffffffffu, pb, off);
+            const bool ok = j >= off;
+            qa = ok ? qa : 1.f;
+            qb = ok ? qb : 0.f;
+            pb = fmaf(pa, qb, pb);   // earlier piece (qa,qb) then ours (pa,pb): (qa pa, pa qb + pb)
+            pa = pa * qa;
+        }
+        ea = __shfl_up_sync(0xffffffffu, pa, 1);
+        eb = __shfl_up_sync(0xffffffffu, pb, 1);
+    } else {
+        for (int off = 1; off < lpr; off <<= 1) {
+            float qa = __shfl_up_sync(0xffffffffu, pa, off, lpr);
+            float qb = __shfl_up_sync(0xffffffffu, pb, off, lpr);
+            const bool ok = j >= off;
+            qa = ok ? qa : 1.f;
+            qb = ok ? qb : 0.f;
+            pb = fmaf(pa, qb, pb);
+            pa = pa * qa;
+        }
+        ea = __shfl_up_sync(0xffffffffu, pa, 1, lpr);
+        eb = __shfl_up_sync(0xffffffffu, pb, 1, lpr);
     }
-    ea = __shfl_up_sync(0xffffffffu, pa, 1, lpr);
-    eb = __shfl_up_sync(0xffffffffu, pb, 1, lpr);
     if (j == 0) { ea = 1.f; eb = 0.f; }
 }
 // Reverse (suffix) scan: G_t = rb_t + ra_t * G_{t+1}.  On return (pa, pb) aggregates lanes [j..lpr-1],
 // (ea, eb) lanes [j+1..lpr-1].
+template <int kLPR>
 __device__ __forceinline__ void seg_scan_rev(float &pa, float &pb, float &ea, float &eb, int j, int lpr) {
-    for (int off = 1; off < lpr; off <<= 1) {
-        float qa = __shfl_down_sync(0xffffffffu, pa, off, lpr);
-        float qb = __shfl_down_sync(0xffffffffu, pb, off, lpr);
-        const bool ok = j + off < lpr;
-        qa = ok ? qa : 1.f;
-        qb = ok ? qb : 0.f;
-        pb = fmaf(pa, qb, pb);
-        pa = pa * qa;
+    if (kLPR == 32) {
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            float qa = __shfl_down_sync(0xffffffffu, pa, off);
+            float qb = __shfl_down_sync(0xffffffffu, pb, off);
+            const bool ok = j + off < 32;
+            qa = ok ? qa : 1.f;
+            qb = ok ? qb : 0.f;
+            pb = fmaf(pa, qb, pb);
+            pa = pa * qa;
+        }
+        ea = __shfl_down_sync(0xffffffffu, pa, 1);
+        eb = __shfl_down_sync(0xffffffffu, pb, 1);
+    } else {
+        for (int off = 1; off < lpr; off <<= 1) {
+            float qa = __shfl_down_sync(0xffffffffu, pa, off, lpr);
+            float qb = __shfl_down_sync(0xffffffffu, pb, off, lpr);
+            const bool ok = j + off < lpr;
+            qa = ok ? qa : 1.f;
+            qb = ok ? qb : 0.f;
+            pb = fmaf(pa, qb, pb);
+            pa = pa * qa;
+        }
+        ea = __shfl_down_sync(0xffffffffu, pa, 1, lpr);
+        eb = __shfl_down_sync(0xffffffffu, pb, 1, lpr);
     }
-    ea = __shfl_down_sync(0xffffffffu, pa, 1, lpr);
-    eb = __shfl_down_sync(0xffffffffu, pb, 1, lpr);
     if (j == lpr - 1) { ea = 1.f; eb = 0.f; }
 }
 
+// sum over the lanes of a row piece; result valid in every lane of the piece
+template <int kLPR>
 __device__ __forceinline__ float seg_sum(float v, int lpr) {
-    for (int off = lpr >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off, lpr);
+    if (kLPR == 32) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    } else {
+        for (int off = lpr >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off, 32);
+    }
     return v;
+}
+// three full-warp sums for the price of six shuffles: on return lane 0 holds sum(a), lane 16 sum(b), lane 8 sum(c)
+__device__ __forceinline__ float warp_sum3(float a, float b, float c, int lane) {
+    const bool hi = lane & 16;
+    float p = (hi ? b : a) + __shfl_xor_sync(0xffffffffu, hi ? a : b, 16);   // lo half: a pairs, hi half: b pairs
+    float q = c + __shfl_xor_sync(0xffffffffu, c, 16);                        // both halves: c pairs
+    const bool b3 = lane & 8;
+    float r = (b3 ? q : p) + __shfl_xor_sync(0xffffffffu, b3 ? p : q, 8);    // bit3 = 0: a|b quads, bit3 = 1: c quads
+    r += __shfl_xor_sync(0xffffffffu, r, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
+
+// zero the dynamic shared memory once per CTA so that padding / not-yet-written bytes read as finite values
+__device__ __forceinline__ void zero_smem(char *smem, int bytes) {
+    uint4 *p = reinterpret_cast<uint4 *>(smem);
+    for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
 }
 
 }  // namespace mia
