@@ -10,8 +10,8 @@
 #include "scan_common.cuh"
 
 namespace mia {
-template <typename T> cudaError_t launch_fwd(const ScanArgs &, int, cudaStream_t);
-template <typename T> cudaError_t launch_bwd(const ScanArgs &, int, cudaStream_t);
+template <typename T> cudaError_t launch_fwd_any(const ScanArgs &, int, cudaStream_t);
+template <typename T> cudaError_t launch_bwd_any(const ScanArgs &, int, cudaStream_t);
 }  // namespace mia
 
 namespace {
@@ -76,14 +76,14 @@ void set_split(Plan &pl, const mia_ss_params &p, int split) {
     pl.n_seg = p.batch * p.n_groups * pl.split;
 }
 
-Plan make_plan(const mia_ss_params &p, int sms) {
+Plan make_plan(const mia_ss_params &p, int sms, bool bwd) {
     Plan pl;
     pl.LPR = lanes_per_row(p.seqlen);
     pl.CH = pl.LPR * mia::kTok;
     pl.n_chunks = (p.seqlen + pl.CH - 1) / pl.CH;
     pl.RPP = 32 / pl.LPR;
-    pl.NW = mia::kThreads / 32 - 1;
-    pl.RT = pl.NW * pl.RPP * 4;   // four row passes per warp and row stage (amortises the per-stage bookkeeping)
+    pl.NW = (bwd ? mia::kThreads : mia::kThreadsFwd) / 32 - 1;
+    pl.RT = pl.NW * pl.RPP * (bwd ? 4 : 3);   // row passes per warp and row stage (amortises the per-stage bookkeeping)
     const int rpg = p.dim / p.n_groups;
     // Segments: (batch, group, row range).  Aim at >= ~6 segments per SM with the best last-wave balance; a segment
     // keeps its carries in shared memory, so bound rows * d_state.
@@ -204,7 +204,7 @@ bool layout_smem(mia::ScanArgs &a, int es, int eso, bool bwd, int smem_max) {
 // Pick the work plan and carve shared memory; if it does not fit, first cut segments finer (smaller carries and
 // parameter blocks), then halve the row tile.
 int plan_and_layout(const mia_ss_params &p, const DeviceInfo &di, bool bwd, Plan &pl, mia::ScanArgs &a) {
-    pl = make_plan(p, di.sms);
+    pl = make_plan(p, di.sms, bwd);
     const int es = esize(p.itype), eso = esize(p.otype);
     const int rpg = p.dim / p.n_groups;
     for (;;) {
@@ -350,7 +350,7 @@ int mia_selective_scan_fwd(const mia_ss_params *pp, void *cuda_stream) {
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     const int rc = dispatch(p.itype, [&](auto *tag) {
         using T = typename std::remove_pointer<decltype(tag)>::type;
-        return (int)mia::launch_fwd<T>(a, grid, stream);
+        return (int)mia::launch_fwd_any<T>(a, grid, stream);
     });
     if (rc != 0) return fail(MIA_ECUDA, "selective_scan_fwd launch: %s", cudaGetErrorString((cudaError_t)rc));
     g_launches.fetch_add(1);
@@ -404,7 +404,7 @@ int mia_selective_scan_bwd(const mia_ss_params *pp, void *cuda_stream) {
     const int grid = a.n_seg < di.sms ? a.n_seg : di.sms;
     int rc = dispatch(p.itype, [&](auto *tag) {
         using T = typename std::remove_pointer<decltype(tag)>::type;
-        return (int)mia::launch_bwd<T>(a, grid, stream);
+        return (int)mia::launch_bwd_any<T>(a, grid, stream);
     });
     if (rc != 0) return fail(MIA_ECUDA, "selective_scan_bwd launch: %s", cudaGetErrorString((cudaError_t)rc));
     g_launches.fetch_add(1);

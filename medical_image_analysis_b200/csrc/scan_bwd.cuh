@@ -29,35 +29,14 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 
 __device__ __forceinline__ void consumer_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
-template <typename T, bool kSoftplus, bool kN1, int kLPR>
-__global__ void __launch_bounds__(kThreads, 1) ss_bwd_kernel(const __grid_constant__ ScanArgs a) {
-    extern __shared__ __align__(128) char smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int NW = a.n_consumer_warps;
-    uint64_t *rfull = reinterpret_cast<uint64_t *>(smem + a.off_bars);
-    uint64_t *rempty = rfull + kMaxStages;
-    uint64_t *gfull = rempty + kMaxStages;
-    uint64_t *gempty = gfull + kGroupStages;
-    const int N = kN1 ? 1 : a.N, L = a.L, CH = a.CH, RT = a.RT, RS = a.RS;
-    float *carryG = reinterpret_cast<float *>(smem + a.off_carry);  // [RS][N] suffix value entering from the next chunk
-    float *carryA = carryG + RS * N;                                // [RS][N] dA accumulated over chunks
-    float *carryD = carryA + RS * N;                                // [RS]
-    float *carryBias = carryD + RS;                                 // [RS]
-    float *red = reinterpret_cast<float *>(smem + a.off_red);       // [NW][256]
+// ===================== producer warp: TMA-stage group + row stages (chunks last-to-first) =====================
+template <typename T>
+__device__ __forceinline__ void bwd_producer(const ScanArgs &a, char *smem, uint64_t *rfull, uint64_t *rempty, uint64_t *gfull,
+                                             uint64_t *gempty, int lane) {
     constexpr int es = (int)sizeof(T);
     const int eso = a.out_f32 ? 4 : es;
-
-    zero_smem(smem, a.smem_bytes);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < a.stages; ++s) { mbar_init(rfull + s, 1); mbar_init(rempty + s, NW); }
-        for (int s = 0; s < kGroupStages; ++s) { mbar_init(gfull + s, 1); mbar_init(gempty + s, NW); }
-        fence_mbar_init();
-    }
-    __syncthreads();
-
-    if (warp == NW) {
-        // ===================== producer warp =====================
+    const int N = a.N, L = a.L, CH = a.CH, RT = a.RT;
+    {
         const float *Ap = reinterpret_cast<const float *>(a.A);
         const float *Dp = reinterpret_cast<const float *>(a.D);
         const float *biasp = reinterpret_cast<const float *>(a.delta_bias);
@@ -120,6 +99,38 @@ __global__ void __launch_bounds__(kThreads, 1) ss_bwd_kernel(const __grid_consta
                 }
             }
         }
+    }
+}
+
+template <typename T, bool kSoftplus, bool kN1, int kLPR>
+__global__ void __launch_bounds__(kThreads, 1) ss_bwd_kernel(const __grid_constant__ ScanArgs a) {
+    extern __shared__ __align__(128) char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NW = a.n_consumer_warps;
+    uint64_t *rfull = reinterpret_cast<uint64_t *>(smem + a.off_bars);
+    uint64_t *rempty = rfull + kMaxStages;
+    uint64_t *gfull = rempty + kMaxStages;
+    uint64_t *gempty = gfull + kGroupStages;
+    const int N = kN1 ? 1 : a.N, L = a.L, CH = a.CH, RT = a.RT, RS = a.RS;
+    float *carryG = reinterpret_cast<float *>(smem + a.off_carry);  // [RS][N] suffix value entering from the next chunk
+    float *carryA = carryG + RS * N;                                // [RS][N] dA accumulated over chunks
+    float *carryD = carryA + RS * N;                                // [RS]
+    float *carryBias = carryD + RS;                                 // [RS]
+    float *red = reinterpret_cast<float *>(smem + a.off_red);       // [NW][256]
+    constexpr int es = (int)sizeof(T);
+    const int eso = a.out_f32 ? 4 : es;
+
+    zero_smem(smem, a.smem_bytes);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(rfull + s, 1); mbar_init(rempty + s, NW); }
+        for (int s = 0; s < kGroupStages; ++s) { mbar_init(gfull + s, 1); mbar_init(gempty + s, NW); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == NW) {
+        bwd_producer<T>(a, smem, rfull, rempty, gfull, gempty, lane);
     } else if (warp < NW) {
         // ===================== consumer warps =====================
         const int LPR = kLPR == 32 ? 32 : a.LPR, RPP = kLPR == 32 ? 1 : 32 / LPR;

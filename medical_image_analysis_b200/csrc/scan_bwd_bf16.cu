@@ -1,5 +1,5 @@
 // bwd selective-scan kernels, bf16 activations (one translation unit per dtype so they compile in parallel)
-#include "scan_bwd.cuh"
+#include "scan_bwd_fast.cuh"
 namespace mia {
-template cudaError_t launch_bwd<__nv_bfloat16>(const ScanArgs &, int, cudaStream_t);
+template cudaError_t launch_bwd_any<__nv_bfloat16>(const ScanArgs &, int, cudaStream_t);
 }  // namespace mia

@@ -1,5 +1,5 @@
 // bwd selective-scan kernels, f16 activations (one translation unit per dtype so they compile in parallel)
-#include "scan_bwd.cuh"
+#include "scan_bwd_fast.cuh"
 namespace mia {
-template cudaError_t launch_bwd<__half>(const ScanArgs &, int, cudaStream_t);
+template cudaError_t launch_bwd_any<__half>(const ScanArgs &, int, cudaStream_t);
 }  // namespace mia

@@ -22,7 +22,8 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr int kMaxStages = 8;
 constexpr int kGroupStages = 2;
-constexpr int kThreads = 512;  // 15 consumer warps + 1 producer: 4 warps per SM sub-partition, 128 registers each
+constexpr int kThreads = 512;     // bwd: 15 consumer warps + 1 producer: 4 warps per SM sub-partition, 128 registers each
+constexpr int kThreadsFwd = 512;
 
 // ------------------------------------------------------------------------------------------------
 // Kernel argument block (built on the host by scan_api.cu).
@@ -188,6 +189,119 @@ __device__ __forceinline__ void st8(void *p, const float (&f)[kTok], int nvalid)
 #pragma unroll
     for (int i = 0; i < kTok; ++i)
         if (i < nvalid) reinterpret_cast<typename Cvt<T>::raw *>(p)[i] = buf.t.v[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Packed f32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 -- two fp32 lanes per issued instruction) and the
+// 8-token <-> 4 x float2 conversions the fast paths are written in.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
+template <int kWords>
+__device__ __forceinline__ void lds_words(uint32_t saddr, uint32_t (&w)[kWords]) {
+    if ((saddr & 15) == 0) {
+#pragma unroll
+        for (int i = 0; i < kWords / 4; ++i)
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[4 * i]), "=r"(w[4 * i + 1]), "=r"(w[4 * i + 2]), "=r"(w[4 * i + 3])
+                         : "r"(saddr + 16 * i));
+    } else if ((saddr & 7) == 0) {
+#pragma unroll
+        for (int i = 0; i < kWords / 2; ++i)
+            asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(w[2 * i]), "=r"(w[2 * i + 1]) : "r"(saddr + 8 * i));
+    } else if ((saddr & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < kWords; ++i) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[i]) : "r"(saddr + 4 * i));
+    } else {   // 2-byte aligned (16-bit types with odd sequence length)
+#pragma unroll
+        for (int i = 0; i < kWords; ++i) {
+            uint16_t lo, hi;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(lo) : "r"(saddr + 4 * i));
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hi) : "r"(saddr + 4 * i + 2));
+            w[i] = (uint32_t)lo | ((uint32_t)hi << 16);
+        }
+    }
+}
+
+template <typename T> struct Vec;   // 8 tokens as 4 float2
+template <> struct Vec<__nv_bfloat16> {
+    static constexpr int kWords = 4;
+    static __device__ __forceinline__ float2 up(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+    static __device__ __forceinline__ void unpack(const uint32_t (&w)[4], float2 (&f)[4]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f[k] = up(w[k]);
+    }
+    static __device__ __forceinline__ void pack(const float2 (&f)[4], uint32_t (&w)[4]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { __nv_bfloat162 h = __floats2bfloat162_rn(f[k].x, f[k].y); w[k] = *reinterpret_cast<uint32_t *>(&h); }
+    }
+};
+template <> struct Vec<__half> {
+    static constexpr int kWords = 4;
+    static __device__ __forceinline__ void unpack(const uint32_t (&w)[4], float2 (&f)[4]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { __half2 h = *reinterpret_cast<const __half2 *>(&w[k]); f[k] = __half22float2(h); }
+    }
+    static __device__ __forceinline__ void pack(const float2 (&f)[4], uint32_t (&w)[4]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { __half2 h = __floats2half2_rn(f[k].x, f[k].y); w[k] = *reinterpret_cast<uint32_t *>(&h); }
+    }
+};
+template <> struct Vec<float> {
+    static constexpr int kWords = 8;
+    static __device__ __forceinline__ void unpack(const uint32_t (&w)[8], float2 (&f)[4]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f[k] = make_float2(__uint_as_float(w[2 * k]), __uint_as_float(w[2 * k + 1]));
+    }
+    static __device__ __forceinline__ void pack(const float2 (&f)[4], uint32_t (&w)[8]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { w[2 * k] = __float_as_uint(f[k].x); w[2 * k + 1] = __float_as_uint(f[k].y); }
+    }
+};
+
+template <typename T>
+__device__ __forceinline__ void lds8v(uint32_t saddr, float2 (&f)[4]) {
+    uint32_t w[Vec<T>::kWords];
+    lds_words<Vec<T>::kWords>(saddr, w);
+    Vec<T>::unpack(w, f);
+}
+
+// store 8 tokens (nvalid of them) to global memory with the widest stores the address allows
+template <typename T>
+__device__ __forceinline__ void st8v(void *p, const float2 (&f)[4], int nvalid) {
+    constexpr int kWords = Vec<T>::kWords;
+    constexpr int kPer = 8 / kWords;     // tokens per 32-bit word
+    uint32_t w[kWords];
+    Vec<T>::pack(f, w);
+    const uintptr_t a = (uintptr_t)p;
+    if (nvalid >= kTok) {
+        if ((a & 15) == 0) {
+#pragma unroll
+            for (int i = 0; i < kWords / 4; ++i) reinterpret_cast<uint4 *>(p)[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+            return;
+        } else if ((a & 7) == 0) {
+#pragma unroll
+            for (int i = 0; i < kWords / 2; ++i) reinterpret_cast<uint2 *>(p)[i] = make_uint2(w[2 * i], w[2 * i + 1]);
+            return;
+        }
+    }
+    if ((a & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < kWords; ++i)
+            if ((i + 1) * kPer <= nvalid) reinterpret_cast<uint32_t *>(p)[i] = w[i];
+        if (kPer == 2 && (nvalid & 1) && nvalid < kTok) {
+#pragma unroll
+            for (int i = 0; i < kWords; ++i)
+                if (2 * i + 1 == nvalid) reinterpret_cast<uint16_t *>(p)[2 * i] = (uint16_t)(w[i] & 0xffffu);
+        }
+        return;
+    }
+    if (kPer == 2) {
+#pragma unroll
+        for (int i = 0; i < kTok; ++i)
+            if (i < nvalid) reinterpret_cast<uint16_t *>(p)[i] = (uint16_t)((w[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -16,31 +16,13 @@
 
 namespace mia {
 
-template <typename T, bool kSoftplus, bool kN1, int kLPR>
-__global__ void __launch_bounds__(kThreads, 1) ss_fwd_kernel(const __grid_constant__ ScanArgs a) {
-    extern __shared__ __align__(128) char smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int NW = a.n_consumer_warps;
-    uint64_t *rfull = reinterpret_cast<uint64_t *>(smem + a.off_bars);
-    uint64_t *rempty = rfull + kMaxStages;
-    uint64_t *gfull = rempty + kMaxStages;
-    uint64_t *gempty = gfull + kGroupStages;
-    float2 *carry = reinterpret_cast<float2 *>(smem + a.off_carry);  // [RS][N] running (prod a, h)
+// ===================== producer warp: TMA-stage group + row stages =====================
+template <typename T>
+__device__ __forceinline__ void fwd_producer(const ScanArgs &a, char *smem, uint64_t *rfull, uint64_t *rempty, uint64_t *gfull,
+                                             uint64_t *gempty, int lane) {
     constexpr int es = (int)sizeof(T);
-
-    zero_smem(smem, a.smem_bytes);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < a.stages; ++s) { mbar_init(rfull + s, 1); mbar_init(rempty + s, NW); }
-        for (int s = 0; s < kGroupStages; ++s) { mbar_init(gfull + s, 1); mbar_init(gempty + s, NW); }
-        fence_mbar_init();
-    }
-    __syncthreads();
-
-    const int N = kN1 ? 1 : a.N, L = a.L, CH = a.CH, RT = a.RT;
-
-    if (warp == NW) {
-        // ===================== producer warp: TMA-stage group + row stages =====================
+    const int N = a.N, L = a.L, CH = a.CH, RT = a.RT;
+    {
         const float *Ap = reinterpret_cast<const float *>(a.A);
         const float *Dp = reinterpret_cast<const float *>(a.D);
         const float *biasp = reinterpret_cast<const float *>(a.delta_bias);
@@ -92,6 +74,34 @@ __global__ void __launch_bounds__(kThreads, 1) ss_fwd_kernel(const __grid_consta
                 }
             }
         }
+    }
+}
+
+template <typename T, bool kSoftplus, bool kN1, int kLPR>
+__global__ void __launch_bounds__(kThreadsFwd, 1) ss_fwd_kernel(const __grid_constant__ ScanArgs a) {
+    extern __shared__ __align__(128) char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NW = a.n_consumer_warps;
+    uint64_t *rfull = reinterpret_cast<uint64_t *>(smem + a.off_bars);
+    uint64_t *rempty = rfull + kMaxStages;
+    uint64_t *gfull = rempty + kMaxStages;
+    uint64_t *gempty = gfull + kGroupStages;
+    float2 *carry = reinterpret_cast<float2 *>(smem + a.off_carry);  // [RS][N] running (prod a, h)
+    constexpr int es = (int)sizeof(T);
+
+    zero_smem(smem, a.smem_bytes);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(rfull + s, 1); mbar_init(rempty + s, NW); }
+        for (int s = 0; s < kGroupStages; ++s) { mbar_init(gfull + s, 1); mbar_init(gempty + s, NW); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int N = kN1 ? 1 : a.N, L = a.L, CH = a.CH, RT = a.RT;
+
+    if (warp == NW) {
+        fwd_producer<T>(a, smem, rfull, rempty, gfull, gempty, lane);
     } else if (warp < NW) {
         // ===================== consumer warps: scan rows =====================
         const int LPR = kLPR == 32 ? 32 : a.LPR, RPP = kLPR == 32 ? 1 : 32 / LPR;
@@ -240,7 +250,7 @@ cudaError_t launch_fwd(const ScanArgs &a, int grid, cudaStream_t stream) {
 #undef MIA_PICK
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
     if (e != cudaSuccess) return e;
-    kernel<<<grid, kThreads, a.smem_bytes, stream>>>(a);
+    kernel<<<grid, kThreadsFwd, a.smem_bytes, stream>>>(a);
     return cudaGetLastError();
 }
 

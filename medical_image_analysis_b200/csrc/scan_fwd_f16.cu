@@ -1,5 +1,5 @@
 // fwd selective-scan kernels, f16 activations (one translation unit per dtype so they compile in parallel)
-#include "scan_fwd.cuh"
+#include "scan_fwd_fast.cuh"
 namespace mia {
-template cudaError_t launch_fwd<__half>(const ScanArgs &, int, cudaStream_t);
+template cudaError_t launch_fwd_any<__half>(const ScanArgs &, int, cudaStream_t);
 }  // namespace mia
