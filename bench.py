@@ -312,10 +312,11 @@ def main():
     bwd_gbs = per_gpu_tokens * bwd_b / (bwd_ms * 1e-3) / 1e9
     fwd_gbs = per_gpu_tokens * fwd_b / (fwd_ms * 1e-3) / 1e9
     step_gbs = (value / world) * (fwd_b + bwd_b) / 1e9
-    roofline = {"bound": "hbm", "kernel": "ss_bwd_kernel<bf16> (+ss_finalize_kernel, timed together as the bwd C-ABI call)",
+    roofline = {"bound": "hbm", "kernel": "backward C-ABI call = ss_bwd_fast_kernel<bf16> + ss_finalize_kernel (timed together)",
                 "achieved": bwd_gbs, "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": per_gpu_tokens * bwd_b,
-                "fwd_kernel": {"achieved": fwd_gbs, "frac": fwd_gbs / peak, "algorithmic_bytes_per_launch": per_gpu_tokens * fwd_b},
+                "fwd_kernel": {"kernel": "forward C-ABI call = ss_fwd_rows_kernel<bf16>", "achieved": fwd_gbs, "frac": fwd_gbs / peak,
+                               "algorithmic_bytes_per_launch": per_gpu_tokens * fwd_b},
                 "step": {"achieved": step_gbs, "frac": step_gbs / peak, "roofline_tokens_per_s": peak * 1e9 / (fwd_b + bwd_b)}}
     line = {"metric": METRIC, "value": value, "unit": "patch-tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -8,8 +8,10 @@
 
 #include "../../include/mia_selective_scan.h"
 #include "scan_common.cuh"
+#include "scan_fwd_rows.cuh"
 
 namespace mia {
+template <typename T> cudaError_t launch_fwd_rows(const RowsArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_fwd_any(const ScanArgs &, int, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_any(const ScanArgs &, int, cudaStream_t);
 }  // namespace mia
@@ -225,6 +227,41 @@ int plan_and_layout(const mia_ss_params &p, const DeviceInfo &di, bool bwd, Plan
     }
 }
 
+// Row-serial forward (scan_fwd_rows.cuh): eligibility + argument block.  Returns false when the warp-scan kernels must run.
+bool plan_rows_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsArgs &r, int &grid) {
+    const int es = esize(p.itype), L = p.seqlen;
+    const int rpg = p.dim / p.n_groups;
+    if (p.dstate != 1 || p.z || p.delta_dim != p.dim || (rpg % 32) || (L % 4)) return false;
+    auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
+    if (!dense(p.u_batch_stride, p.u_d_stride) || !dense(p.delta_batch_stride, p.delta_d_stride) ||
+        !dense(p.out_batch_stride, p.out_d_stride)) return false;
+    if (p.A_d_stride != 1 && p.dim > 1) return false;
+    if (((uintptr_t)p.u | (uintptr_t)p.delta | (uintptr_t)p.out) & 15) return false;
+    memset(&r, 0, sizeof(r));
+    const int budget = 13 * 1024;                               // bytes of one [32 x chunk] tile (8 warps per SM at 2-byte dtypes)
+    int Lc = L;
+    if (32 * L * es > budget) {
+        if ((L * es) % 16) return false;                        // per-row pieces must start 16-byte aligned
+        Lc = budget / (32 * es) / 8 * 8;
+    }
+    r.batch = p.batch; r.dim = p.dim; r.L = L; r.G = p.n_groups; r.rows_per_group = rpg; r.softplus = p.delta_softplus;
+    r.Lc = Lc; r.n_lchunks = (L + Lc - 1) / Lc;
+    r.n_items = p.batch * p.n_groups * (rpg / 32);
+    r.tile_bytes = round_up(32 * Lc * es, 128);
+    r.bc_bytes = 0;
+    r.off_bc32 = 2 * r.tile_bytes;
+    r.stage_bytes = r.off_bc32 + round_up(2 * Lc * 4, 128);
+    r.smem_bytes = r.stage_bytes + 128;
+    if (r.smem_bytes > di.smem_optin) return false;
+    r.xchunks = mia_ss_num_chunks(L); r.xchunk_tokens = mia_ss_chunk_len(L);
+    r.u = p.u; r.delta = p.delta; r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.out = p.out; r.x = p.x;
+    r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride;
+    const int per_sm = di.smem_optin / (r.smem_bytes + 1024) > 0 ? (227 * 1024) / (r.smem_bytes + 1024) : 1;
+    grid = di.sms * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
+    if (grid > r.n_items) grid = r.n_items;
+    return true;
+}
+
 template <typename F>
 int dispatch(int itype, F &&f) {
     switch (itype) {
@@ -341,13 +378,27 @@ int mia_selective_scan_fwd(const mia_ss_params *pp, void *cuda_stream) {
     MIA_CHECK(!p.z || p.out_z, "out_z is required when z is given");
     DeviceInfo di;
     if (int rc = device_info(di)) return rc;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    {
+        mia::RowsArgs r;
+        int rgrid = 0;
+        if (plan_rows_fwd(p, di, r, rgrid)) {
+            const bool of32 = p.otype == MIA_F32 && p.itype != MIA_F32;
+            const int rc = dispatch(p.itype, [&](auto *tag) {
+                using T = typename std::remove_pointer<decltype(tag)>::type;
+                return (int)mia::launch_fwd_rows<T>(r, rgrid, of32, stream);
+            });
+            if (rc != 0) return fail(MIA_ECUDA, "selective_scan_fwd (row-serial) launch: %s", cudaGetErrorString((cudaError_t)rc));
+            g_launches.fetch_add(1);
+            return MIA_OK;
+        }
+    }
     Plan pl;
     mia::ScanArgs a;
     if (int rc = plan_and_layout(p, di, false, pl, a)) return rc;
     a.out = p.out; a.out_z = p.out_z;
     a.out_bs = p.out_batch_stride; a.out_ds = p.out_d_stride; a.outz_bs = p.out_z_batch_stride; a.outz_ds = p.out_z_d_stride;
     const int grid = a.n_seg < di.sms ? a.n_seg : di.sms;
-    cudaStream_t stream = (cudaStream_t)cuda_stream;
     const int rc = dispatch(p.itype, [&](auto *tag) {
         using T = typename std::remove_pointer<decltype(tag)>::type;
         return (int)mia::launch_fwd_any<T>(a, grid, stream);
