@@ -116,7 +116,13 @@ size_t mia_selective_scan_bwd_workspace(const mia_ss_params *p);
  * casts (:347) and delta-group folds (:348-353). */
 int mia_selective_scan_bwd(const mia_ss_params *p, void *cuda_stream);
 
-/* Number of kernel launches issued by this library on the calling thread since load (bench.py's gpu_launches). */
+/* CrossScan / CrossMerge of SS2D (R2GenCSR/VMamba/classification/models/vmamba.py:25-67, csm_triton.py:163-235).
+ * x, y: (batch, channels, H, W) contiguous; xs, ys: (batch, 4, channels, H*W) contiguous; same dtype in and out.
+ * scan: xs[:,0] = row-major, xs[:,1] = column-major, xs[:,2:4] = their reversals.  merge = its adjoint (fp32 sum). */
+int mia_cross_scan(const void *x, void *xs, int batch, int channels, int H, int W, int dtype, void *cuda_stream);
+int mia_cross_merge(const void *ys, void *y, int batch, int channels, int H, int W, int dtype, void *cuda_stream);
+
+/* Number of selective-scan kernel launches issued by this library in this process since load (bench.py gpu_launches). */
 uint64_t mia_launch_count(void);
 
 #ifdef __cplusplus

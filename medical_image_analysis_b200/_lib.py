@@ -62,6 +62,9 @@ def lib() -> ctypes.CDLL:
         L.mia_selective_scan_bwd.restype = ctypes.c_int
         L.mia_selective_scan_bwd_workspace.argtypes = [ctypes.POINTER(MiaSSParams)]
         L.mia_selective_scan_bwd_workspace.restype = ctypes.c_size_t
+        for fn in (L.mia_cross_scan, L.mia_cross_merge):
+            fn.argtypes = [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]
+            fn.restype = ctypes.c_int
         if L.mia_abi_version() != 1:
             raise RuntimeError(f"libmia_scan.so ABI version {L.mia_abi_version()} != 1: rebuild it")
         _lib = L

@@ -1,0 +1,312 @@
+"""SS2D (VMamba's 2-D selective-scan block) on the B200 kernels.
+
+Mirrors the module surface of R2GenCSR/VMamba/classification/models/vmamba.py: ``CrossScan`` / ``CrossMerge`` (:25-67),
+``cross_selective_scan`` (:318-427) and ``SS2D`` with the v2 family of ``forward_type`` strings (:540-584, 662-802,
+1092-1129) -- same constructor arguments, same parameter names and shapes (``x_proj_weight (K, R+2N, D)``,
+``dt_projs_weight (K, D, R)``, ``dt_projs_bias (K, D)``, ``A_logs (K*D, N)``, ``Ds (K*D)``, ``in_proj``, ``conv2d``,
+``out_norm``, ``out_proj``) so published VMamba checkpoints load unchanged.  The four scan orders and their merge run as
+single-pass CUDA kernels (csrc/cross_scan.cu) instead of torch copies / Triton; the scan is ``SelectiveScanOflex/Core/Mamba``
+from ``selective_scan_interface``; the projections are library GEMMs.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from functools import partial
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from .selective_scan_interface import SelectiveScanCore, SelectiveScanMamba, SelectiveScanOflex
+
+_DT = {torch.float32: _lib.MIA_F32, torch.float16: _lib.MIA_F16, torch.bfloat16: _lib.MIA_BF16}
+
+
+def _cs_call(fn, src: torch.Tensor, dst: torch.Tensor, B: int, C: int, H: int, W: int) -> None:
+    if not src.is_cuda:
+        raise RuntimeError("CrossScan / CrossMerge need CUDA tensors (there is no CPU fallback)")
+    if src.dtype not in _DT:
+        raise RuntimeError("CrossScan / CrossMerge support float32, float16 and bfloat16")
+    with torch.cuda.device(src.device):
+        stream = ctypes.c_void_p(torch.cuda.current_stream(src.device).cuda_stream)
+        _lib.check(fn(src.data_ptr(), dst.data_ptr(), B, C, H, W, _DT[src.dtype], stream), "cross scan/merge")
+
+
+def cross_scan_fwd(x: torch.Tensor) -> torch.Tensor:
+    """(B, C, H, W) -> (B, 4, C, H*W): row-major, column-major and their reversals (vmamba.py:28-35)."""
+    B, C, H, W = x.shape
+    x = x.contiguous()
+    xs = x.new_empty((B, 4, C, H * W))
+    _cs_call(_lib.lib().mia_cross_scan, x, xs, B, C, H, W)
+    return xs
+
+
+def cross_merge_fwd(ys: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """(B, 4, C, H*W) -> (B, C, H*W): adjoint of cross_scan_fwd (vmamba.py:51-57), summed in fp32."""
+    B, K, C, L = ys.shape
+    ys = ys.contiguous()
+    y = ys.new_empty((B, C, L))
+    _cs_call(_lib.lib().mia_cross_merge, ys, y, B, C, H, W)
+    return y
+
+
+class CrossScan(torch.autograd.Function):
+    """vmamba.py:25-45."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor):
+        B, C, H, W = x.shape
+        ctx.shape = (B, C, H, W)
+        return cross_scan_fwd(x)
+
+    @staticmethod
+    def backward(ctx, ys: torch.Tensor):
+        B, C, H, W = ctx.shape
+        return cross_merge_fwd(ys, H, W).view(B, -1, H, W)
+
+
+class CrossMerge(torch.autograd.Function):
+    """vmamba.py:48-67."""
+
+    @staticmethod
+    def forward(ctx, ys: torch.Tensor):
+        B, K, D, H, W = ys.shape
+        ctx.shape = (H, W)
+        return cross_merge_fwd(ys.view(B, K, D, -1), H, W)
+
+    @staticmethod
+    def backward(ctx, x: torch.Tensor):
+        H, W = ctx.shape
+        B, C, L = x.shape
+        return cross_scan_fwd(x.view(B, C, H, W)).view(B, 4, C, H, W)
+
+
+def cross_selective_scan(x, x_proj_weight, x_proj_bias, dt_projs_weight, dt_projs_bias, A_logs, Ds, delta_softplus=True,
+                         out_norm=None, out_norm_shape="v0", channel_first=False, to_dtype=True, force_fp32=False,
+                         nrows=-1, backnrows=-1, ssoflex=True, SelectiveScan=None, CrossScan=CrossScan, CrossMerge=CrossMerge,
+                         no_einsum=False, dt_low_rank=True):
+    """vmamba.py:318-427 (the low-rank-dt paths; out_norm is whatever fits (B, L, C) or (B, C, H, W))."""
+    B, D, H, W = x.shape
+    D, N = A_logs.shape
+    K, D, R = dt_projs_weight.shape
+    L = H * W
+    if not dt_low_rank:
+        raise NotImplementedError("dt_low_rank=False is not used by any configuration of the reference")
+    SelectiveScan = SelectiveScan or SelectiveScanOflex
+
+    xs = CrossScan.apply(x)                                                            # :385
+    if no_einsum:                                                                      # :379-383
+        x_dbl = F.conv1d(xs.view(B, -1, L), x_proj_weight.view(-1, D, 1),
+                         bias=(x_proj_bias.view(-1) if x_proj_bias is not None else None), groups=K)
+        dts, Bs, Cs = torch.split(x_dbl.view(B, K, -1, L), [R, N, N], dim=2)
+        dts = F.conv1d(dts.contiguous().view(B, -1, L), dt_projs_weight.view(K * D, -1, 1), groups=K)
+    else:                                                                              # :386-390
+        x_dbl = torch.einsum("b k d l, k c d -> b k c l", xs, x_proj_weight)
+        if x_proj_bias is not None:
+            x_dbl = x_dbl + x_proj_bias.view(1, K, -1, 1)
+        dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
+        dts = torch.einsum("b k r l, k d r -> b k d l", dts, dt_projs_weight)
+
+    xs = xs.view(B, -1, L)
+    dts = dts.contiguous().view(B, -1, L)
+    As = -torch.exp(A_logs.to(torch.float))                                            # :394
+    Bs = Bs.contiguous().view(B, K, N, L)
+    Cs = Cs.contiguous().view(B, K, N, L)
+    Ds = Ds.to(torch.float)
+    delta_bias = dt_projs_bias.view(-1).to(torch.float)
+    if force_fp32:                                                                     # :400-404
+        xs, dts, Bs, Cs = xs.to(torch.float), dts.to(torch.float), Bs.to(torch.float), Cs.to(torch.float)
+
+    ys = SelectiveScan.apply(xs, dts, As, Bs, Cs, Ds, delta_bias, delta_softplus, nrows, backnrows, ssoflex).view(B, K, -1, H, W)
+    y = CrossMerge.apply(ys)                                                           # :410
+
+    if channel_first:                                                                  # :412-419
+        y = y.view(B, -1, H, W)
+        if out_norm_shape in ["v1"]:
+            y = out_norm(y)
+        else:
+            y = out_norm(y.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+        return y.to(x.dtype) if to_dtype else y
+    y = y.to(torch.bfloat16)                                                           # :420 (unconditional in the reference)
+    if not torch.is_autocast_enabled() and isinstance(out_norm, nn.LayerNorm) and out_norm.weight is not None:
+        y = y.to(out_norm.weight.dtype)   # the reference only runs this under bf16 autocast; keep the rounding, not the dtype clash
+    if out_norm_shape in ["v1"]:
+        y = out_norm(y.view(B, -1, H, W)).permute(0, 2, 3, 1)
+    else:
+        y = out_norm(y.transpose(dim0=1, dim1=2).contiguous()).view(B, H, W, -1)
+    return y.to(x.dtype) if to_dtype else y
+
+
+class Linear2d(nn.Linear):
+    """vmamba.py:441-448: a 1x1 conv that loads Linear or Conv2d weights."""
+
+    def forward(self, x: torch.Tensor):
+        return F.conv2d(x, self.weight[:, :, None, None], self.bias)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        state_dict[prefix + "weight"] = state_dict[prefix + "weight"].view(self.weight.shape)
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+
+class LayerNorm2d(nn.LayerNorm):
+    """vmamba.py:451-456."""
+
+    def forward(self, x: torch.Tensor):
+        x = x.permute(0, 2, 3, 1)
+        x = F.layer_norm(x, self.normalized_shape, self.weight, self.bias, self.eps)
+        return x.permute(0, 3, 1, 2)
+
+
+class SS2D(nn.Module):
+    """vmamba.py:540-802 (``__initv2__``) + 1092-1129 (``forward_corev2`` / ``forwardv2``)."""
+
+    def __init__(self, d_model=96, d_state=16, ssm_ratio=2.0, dt_rank="auto", act_layer=nn.SiLU, d_conv=3, conv_bias=True,
+                 dropout=0.0, bias=False, dt_min=0.001, dt_max=0.1, dt_init="random", dt_scale=1.0, dt_init_floor=1e-4,
+                 initialize="v0", forward_type="v2", channel_first=False, **kwargs):
+        super().__init__()
+        if forward_type.startswith("v0") or forward_type.startswith("xv"):
+            raise NotImplementedError("the legacy v0 / experimental xv forward types are not part of the accelerated path")
+        d_inner = int(ssm_ratio * d_model)
+        dt_rank = math.ceil(d_model / 16) if dt_rank == "auto" else dt_rank
+        self.d_conv = d_conv
+        self.channel_first = channel_first
+        Linear = Linear2d if channel_first else nn.Linear
+
+        def checkpostfix(tag, value):
+            ret = value[-len(tag):] == tag
+            return ret, (value[:-len(tag)] if ret else value)
+
+        self.disable_force32, forward_type = checkpostfix("no32", forward_type)
+        self.disable_z, forward_type = checkpostfix("noz", forward_type)
+        self.disable_z_act, forward_type = checkpostfix("nozact", forward_type)
+
+        self.out_norm_shape = "v1"
+        if forward_type.endswith("none"):
+            forward_type = forward_type[:-len("none")]
+            self.out_norm = nn.Identity()
+        elif forward_type.endswith("dwconv3"):
+            forward_type = forward_type[:-len("dwconv3")]
+            self.out_norm = nn.Conv2d(d_inner, d_inner, kernel_size=3, padding=1, groups=d_inner, bias=False)
+        elif forward_type.endswith("softmax"):
+            forward_type = forward_type[:-len("softmax")]
+
+            class SoftmaxSpatial(nn.Softmax):
+                def forward(self, x: torch.Tensor):
+                    B, C, H, W = x.shape
+                    return super().forward(x.view(B, C, -1)).view(B, C, H, W)
+            self.out_norm = SoftmaxSpatial(dim=-1)
+        elif forward_type.endswith("sigmoid"):
+            forward_type = forward_type[:-len("sigmoid")]
+            self.out_norm = nn.Sigmoid()
+        elif channel_first:
+            self.out_norm = LayerNorm2d(d_inner)
+        else:
+            self.out_norm_shape = "v0"
+            self.out_norm = nn.LayerNorm(d_inner)
+
+        FORWARD_TYPES = dict(
+            v01=partial(self.forward_corev2, force_fp32=(not self.disable_force32), SelectiveScan=SelectiveScanMamba),
+            v2=partial(self.forward_corev2, force_fp32=(not self.disable_force32), SelectiveScan=SelectiveScanCore),
+            v3=partial(self.forward_corev2, force_fp32=False, SelectiveScan=SelectiveScanOflex),
+            v4=partial(self.forward_corev2, force_fp32=False, SelectiveScan=SelectiveScanOflex, no_einsum=True),
+            v1=partial(self.forward_corev2, force_fp32=True, SelectiveScan=SelectiveScanOflex),
+        )
+        self.forward_core = FORWARD_TYPES.get(forward_type, None)
+        if self.forward_core is None:
+            raise NotImplementedError(f"forward_type {forward_type!r} (ablation / legacy variants are out of scope)")
+        k_group = 4
+
+        d_proj = d_inner if self.disable_z else (d_inner * 2)
+        self.in_proj = Linear(d_model, d_proj, bias=bias)
+        self.act = act_layer()
+        if d_conv > 1:
+            self.conv2d = nn.Conv2d(d_inner, d_inner, groups=d_inner, bias=conv_bias, kernel_size=d_conv, padding=(d_conv - 1) // 2)
+        x_proj = [nn.Linear(d_inner, dt_rank + d_state * 2, bias=False) for _ in range(k_group)]
+        self.x_proj_weight = nn.Parameter(torch.stack([t.weight for t in x_proj], dim=0))         # (K, R + 2N, inner)
+        self.out_proj = Linear(d_inner, d_model, bias=bias)
+        self.dropout = nn.Dropout(dropout) if dropout > 0.0 else nn.Identity()
+
+        if initialize == "v0":
+            dt_projs = [self.dt_init(dt_rank, d_inner, dt_scale, dt_init, dt_min, dt_max, dt_init_floor) for _ in range(k_group)]
+            self.dt_projs_weight = nn.Parameter(torch.stack([t.weight for t in dt_projs], dim=0))   # (K, inner, rank)
+            self.dt_projs_bias = nn.Parameter(torch.stack([t.bias for t in dt_projs], dim=0))       # (K, inner)
+            self.A_logs = self.A_log_init(d_state, d_inner, copies=k_group, merge=True)               # (K * D, N)
+            self.Ds = self.D_init(d_inner, copies=k_group, merge=True)                                # (K * D)
+        elif initialize == "v1":
+            self.Ds = nn.Parameter(torch.ones(k_group * d_inner))
+            self.A_logs = nn.Parameter(torch.randn(k_group * d_inner, d_state))
+            self.dt_projs_weight = nn.Parameter(torch.randn(k_group, d_inner, dt_rank))
+            self.dt_projs_bias = nn.Parameter(torch.randn(k_group, d_inner))
+        elif initialize == "v2":
+            self.Ds = nn.Parameter(torch.ones(k_group * d_inner))
+            self.A_logs = nn.Parameter(torch.zeros(k_group * d_inner, d_state))
+            self.dt_projs_weight = nn.Parameter(0.1 * torch.rand(k_group, d_inner, dt_rank))
+            self.dt_projs_bias = nn.Parameter(0.1 * torch.rand(k_group, d_inner))
+        else:
+            raise NotImplementedError(initialize)
+
+    @staticmethod
+    def dt_init(dt_rank, d_inner, dt_scale=1.0, dt_init="random", dt_min=0.001, dt_max=0.1, dt_init_floor=1e-4):
+        """vmamba.py:964-989: dt_proj whose bias is softplus^-1 of a log-uniform dt in [dt_min, dt_max]."""
+        dt_proj = nn.Linear(dt_rank, d_inner, bias=True)
+        std = dt_rank ** -0.5 * dt_scale
+        if dt_init == "constant":
+            nn.init.constant_(dt_proj.weight, std)
+        elif dt_init == "random":
+            nn.init.uniform_(dt_proj.weight, -std, std)
+        else:
+            raise NotImplementedError(dt_init)
+        dt = torch.exp(torch.rand(d_inner) * (math.log(dt_max) - math.log(dt_min)) + math.log(dt_min)).clamp(min=dt_init_floor)
+        inv_dt = dt + torch.log(-torch.expm1(-dt))
+        with torch.no_grad():
+            dt_proj.bias.copy_(inv_dt)
+        return dt_proj
+
+    @staticmethod
+    def A_log_init(d_state, d_inner, copies=-1, device=None, merge=True):
+        """vmamba.py:991-1005: S4D-real, A = -(1..N)."""
+        A_log = torch.log(torch.arange(1, d_state + 1, dtype=torch.float32, device=device)).repeat(d_inner, 1)
+        if copies > 0:
+            A_log = A_log.unsqueeze(0).repeat(copies, 1, 1)
+            if merge:
+                A_log = A_log.flatten(0, 1)
+        A_log = nn.Parameter(A_log.contiguous())
+        A_log._no_weight_decay = True
+        return A_log
+
+    @staticmethod
+    def D_init(d_inner, copies=-1, device=None, merge=True):
+        """vmamba.py:1007-1017."""
+        D = torch.ones(d_inner, device=device)
+        if copies > 0:
+            D = D.unsqueeze(0).repeat(copies, 1)
+            if merge:
+                D = D.flatten(0, 1)
+        D = nn.Parameter(D)
+        D._no_weight_decay = True
+        return D
+
+    def forward_corev2(self, x: torch.Tensor, cross_selective_scan=cross_selective_scan, **kwargs):
+        """vmamba.py:1092-1108."""
+        return cross_selective_scan(x, self.x_proj_weight, None, self.dt_projs_weight, self.dt_projs_bias, self.A_logs, self.Ds,
+                                    delta_softplus=True, out_norm=getattr(self, "out_norm", None), channel_first=self.channel_first,
+                                    out_norm_shape=getattr(self, "out_norm_shape", "v0"), **kwargs)
+
+    def forward(self, x: torch.Tensor, **kwargs):
+        """vmamba.py:1110-1129 (forwardv2)."""
+        x = self.in_proj(x)
+        if not self.disable_z:
+            x, z = x.chunk(2, dim=(1 if self.channel_first else -1))
+            if not self.disable_z_act:
+                z = self.act(z)
+        if not self.channel_first:
+            x = x.permute(0, 3, 1, 2).contiguous()
+        if self.d_conv > 1:
+            x = self.conv2d(x)
+        x = self.act(x)
+        y = self.forward_core(x)
+        if not self.disable_z:
+            y = y * z
+        return self.dropout(self.out_proj(y))
