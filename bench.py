@@ -53,6 +53,22 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture of this same command (profiles/*_ncu_summary.json); None if no capture is committed."""
+    import glob
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json")), reverse=True):
+        try:
+            d = json.load(open(f))[kernel_key]
+            rd = float(d["dram__bytes_read.sum"].split()[0]); wr = float(d["dram__bytes_write.sum"].split()[0])
+            unit = d["dram__bytes_read.sum"].split()[1]
+            mult = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
+            return (rd + wr) * mult, os.path.basename(f)
+        except Exception:
+            continue
+    return None, None
+
+
 def make_inputs(w, device, seed=0, dtype=torch.bfloat16):
     """Reference generators (test_selective_scan.py:409-444)."""
     g = torch.Generator(device="cpu").manual_seed(seed)
@@ -82,7 +98,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+                                          "-lms", "20"], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -145,37 +161,73 @@ def run_device_steps(inp, steps, warmup, dist_grads=None):
     return total, fwd, bwd
 
 
-def run_e2e_steps(w, inp, steps, warmup):
-    """Same calls, but every step starts from pinned host buffers and ends with the results in host memory."""
+def run_e2e_steps(w, inp, steps, warmup, n_slices=4):
+    """Same C-ABI calls, but every step starts from pinned HOST buffers and ends with the results in host memory.
+    The batch is cut into slices that flow through three streams (H2D -> fwd+bwd -> D2H) so that the two PCIe
+    directions and the kernels overlap; every byte of every step still crosses the bus inside the timed region."""
     from medical_image_analysis_b200 import scan_bwd, scan_fwd
     out_f32 = w["out_f32"]
-    host_in = {k: inp[k].cpu().pin_memory() for k in ("u", "delta", "B", "C", "dout")}
-    dev_in = {k: torch.empty_like(inp[k]) for k in host_in}
+    names = ("u", "delta", "B", "C", "dout")
+    B = w["B"]
+    n_slices = max(1, min(n_slices, B))
+    bounds = [(i * B // n_slices, (i + 1) * B // n_slices) for i in range(n_slices)]
+    host_in = {k: inp[k].cpu().pin_memory() for k in names}
+    dev_in = {k: torch.empty_like(inp[k]) for k in names}
     h2d = sum(t.numel() * t.element_size() for t in host_in.values())
-    host_out = None
+    s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    host_out = {}
     d2h = 0
+    keep = []
+    prev_cmp = [None] * n_slices      # the compute that last read slice i: its inputs may only be overwritten afterwards
 
-    def one():
-        nonlocal host_out, d2h
-        for k in host_in:
-            dev_in[k].copy_(host_in[k], non_blocking=True)
-        out, x, _ = scan_fwd(dev_in["u"], dev_in["delta"], inp["A"], dev_in["B"], dev_in["C"], inp["D"], None, inp["bias"], True, out_f32)
-        g = scan_bwd(dev_in["u"], dev_in["delta"], inp["A"], dev_in["B"], dev_in["C"], inp["D"], None, inp["bias"], dev_in["dout"], x, None, True)
-        res = [out] + [t for t in g if t is not None]
-        if host_out is None:
-            host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res]
-            d2h = sum(t.numel() * t.element_size() for t in res)
-        for h, t in zip(host_out, res):
-            h.copy_(t, non_blocking=True)
+    def one(first=False):
+        nonlocal d2h
+        keep.clear()
+        if first:
+            d2h = 0
+        for si, (lo, hi) in enumerate(bounds):
+            ev_in = torch.cuda.Event()
+            with torch.cuda.stream(s_in):
+                if prev_cmp[si] is not None:
+                    s_in.wait_event(prev_cmp[si])
+                for k in names:
+                    dev_in[k][lo:hi].copy_(host_in[k][lo:hi], non_blocking=True)
+                ev_in.record()
+            ev_cmp = torch.cuda.Event()
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_in)
+                sl = {k: dev_in[k][lo:hi] for k in names}
+                out, x, _ = scan_fwd(sl["u"], sl["delta"], inp["A"], sl["B"], sl["C"], inp["D"], None, inp["bias"], True, out_f32)
+                g = scan_bwd(sl["u"], sl["delta"], inp["A"], sl["B"], sl["C"], inp["D"], None, inp["bias"], sl["dout"], x, None, True)
+                res = [out] + [t for t in g if t is not None]
+                ev_cmp.record()
+            prev_cmp[si] = ev_cmp
+            keep.append(res)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_cmp)
+                for j, t in enumerate(res):
+                    key = (si, j)
+                    if key not in host_out:
+                        host_out[key] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                    if first:
+                        d2h += t.numel() * t.element_size()
+                    host_out[key].copy_(t, non_blocking=True)
+                    t.record_stream(s_out)
 
-    for _ in range(max(1, warmup)):
+    cur = torch.cuda.current_stream()
+    one(first=True)
+    for _ in range(max(0, warmup - 1)):
         one()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
-    e0.record()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(cur)
+    for s_ in (s_in, s_cmp, s_out):
+        s_.wait_stream(cur)
     for _ in range(steps):
         one()
-    e1.record()
+    for s_ in (s_in, s_cmp, s_out):
+        cur.wait_stream(s_)
+    e1.record(cur)
     torch.cuda.synchronize()
     return e0.elapsed_time(e1), h2d, d2h
 
@@ -313,7 +365,8 @@ def main():
     fwd_gbs = per_gpu_tokens * fwd_b / (fwd_ms * 1e-3) / 1e9
     step_gbs = (value / world) * (fwd_b + bwd_b) / 1e9
     roofline = {"bound": "hbm", "kernel": "backward C-ABI call = ss_bwd_fast_kernel<bf16> + ss_finalize_kernel (timed together)",
-                "achieved": bwd_gbs, "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak, "traffic": None,
+                "achieved": bwd_gbs, "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak,
+                "traffic": (ncu_traffic("bwd")[0] if args.workload == DEFAULT else None), "traffic_source": ncu_traffic("bwd")[1],
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": per_gpu_tokens * bwd_b,
                 "fwd_kernel": {"kernel": "forward C-ABI call = ss_fwd_rows_kernel<bf16>", "achieved": fwd_gbs, "frac": fwd_gbs / peak,
                                "algorithmic_bytes_per_launch": per_gpu_tokens * fwd_b},
