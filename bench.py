@@ -86,47 +86,57 @@ def make_inputs(w, device, seed=0, dtype=torch.bfloat16):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled every ~2 ms from a
+    background thread (the timed region is only a few ms long, too short for `nvidia-smi -lms`)."""
 
     def __init__(self, index):
-        self.index, self.proc, self.path = index, None, None
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = False
+        self._thread = None
+
+    def _loop(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # torchrun / CUDA_VISIBLE_DEVICES: map the logical index to the physical device through its UUID
+            uuid = torch.cuda.get_device_properties(self.index).uuid
+            try:
+                h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                    "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            while not self._stop:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.002)
+        except Exception as e:   # report, never hide
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
 
     def start(self):
-        try:
-            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
-            self.path = f.name
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20"], stdout=f, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        import threading
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
+
+    def mark(self):
+        """Only samples taken after this call (the start of the timed region) are reported."""
+        self._mark = len(self.samples)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path).read().splitlines():
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        os.unlink(self.path)
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        self._stop = True
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        smp = self.samples[getattr(self, "_mark", 0):] or self.samples
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(smp)}
+        if smp:
+            out["sm_mhz"] = statistics.median(smp)
         return out
 
 
@@ -301,6 +311,7 @@ def main():
         if rank != 0:
             return
         steps = max(1, args.steps)
+        torch.set_num_threads(os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1: use every host core
         value, ms, sample, cores = cpu_reference_run(w, steps, min(args.warmup, 1))
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "patch-tokens/s", "n_gpus": args.gpus, "steps": steps,
                 "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -335,6 +346,8 @@ def main():
     sampler.start()
     # a short sustained pre-roll so nvidia-smi sees load, then the measured region
     run_device_steps(inp, max(3, args.warmup), 0, dist_grads)
+    time.sleep(0.02)                       # let the NVML thread come up before the timed region
+    sampler.mark()
     launches0 = _lib.launch_count()
     total_ms, fwd_ms, bwd_ms = run_device_steps(inp, args.steps, 0, dist_grads)
     launches = _lib.launch_count() - launches0
@@ -398,6 +411,7 @@ def main():
         line["extra_workloads"] = extras
 
     if not args.no_cpu:
+        torch.set_num_threads(os.cpu_count() or 1)
         cv, cms, sample, cores = cpu_reference_run(w, 2, 0, budget_s=20.0)
         line["cpu_baseline"] = {"value": cv, "unit": "patch-tokens/s", "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(line))
