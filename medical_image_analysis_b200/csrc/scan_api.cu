@@ -8,10 +8,11 @@
 
 #include "../../include/mia_selective_scan.h"
 #include "scan_common.cuh"
-#include "scan_fwd_rows.cuh"
+#include "scan_bwd_rows.cuh"
 
 namespace mia {
 template <typename T> cudaError_t launch_fwd_rows(const RowsArgs &, int, bool, cudaStream_t);
+template <typename T> cudaError_t launch_bwd_rows(const RowsBwdArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_fwd_any(const ScanArgs &, int, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_any(const ScanArgs &, int, cudaStream_t);
 }  // namespace mia
@@ -116,8 +117,12 @@ WorkspaceLayout workspace_layout(const mia_ss_params &p, const Plan &pl) {
     w.part_dA = take((size_t)p.batch * p.dim * p.dstate);
     w.part_dD = take((size_t)p.batch * p.dim);
     w.part_dbias = take((size_t)p.batch * p.dim);
-    size_t nacc = w.bc_atomic ? (size_t)p.batch * p.n_groups * p.dstate * ((p.seqlen + 3) & ~3)
-                              : (size_t)pl.n_seg * p.dstate * p.seqlen;
+    // d_state == 1: one partial row per segment (warp-scan kernels) or per 32-row batch (row-serial kernel); the query
+    // cannot know which of the two will run (it depends on strides and alignment), so size for the larger.
+    const int rpg = p.dim / p.n_groups;
+    const size_t row_items = (p.dstate == 1 && rpg % 32 == 0) ? (size_t)p.batch * p.n_groups * (rpg / 32) : 0;
+    const size_t parts = row_items > (size_t)pl.n_seg ? row_items : (size_t)pl.n_seg;
+    size_t nacc = w.bc_atomic ? (size_t)p.batch * p.n_groups * p.dstate * ((p.seqlen + 3) & ~3) : parts * p.dstate * p.seqlen;
     w.acc_dB = take(nacc);
     w.acc_dC = take(nacc);
     w.acc_bytes = nacc * 4;
@@ -258,6 +263,40 @@ bool plan_rows_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsArgs &
     r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride;
     const int per_sm = di.smem_optin / (r.smem_bytes + 1024) > 0 ? (227 * 1024) / (r.smem_bytes + 1024) : 1;
     grid = di.sms * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
+    if (grid > r.n_items) grid = r.n_items;
+    return true;
+}
+
+// Row-serial backward (scan_bwd_rows.cuh): eligibility + argument block.  Returns false when the warp-scan kernels must run.
+bool plan_rows_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsBwdArgs &r, int &grid) {
+    const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
+    const int rpg = p.dim / p.n_groups;
+    if (p.dstate != 1 || p.z || p.delta_dim != p.dim || (rpg % 32) || (L % 4) || L > 256) return false;
+    auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
+    if (!dense(p.u_batch_stride, p.u_d_stride) || !dense(p.delta_batch_stride, p.delta_d_stride) ||
+        !dense(p.dout_batch_stride, p.dout_d_stride) || !dense(p.du_batch_stride, p.du_d_stride) ||
+        !dense(p.ddelta_batch_stride, p.ddelta_d_stride)) return false;
+    if (p.A_d_stride != 1 && p.dim > 1) return false;
+    if (((uintptr_t)p.u | (uintptr_t)p.delta | (uintptr_t)p.dout | (uintptr_t)p.du | (uintptr_t)p.ddelta) & 15) return false;
+    memset(&r, 0, sizeof(r));
+    r.batch = p.batch; r.dim = p.dim; r.L = L; r.G = p.n_groups; r.rows_per_group = rpg; r.softplus = p.delta_softplus;
+    r.nblk = (L + mia::kBlk - 1) / mia::kBlk;
+    r.Lp = r.nblk * mia::kBlk;
+    r.n_items = p.batch * p.n_groups * (rpg / 32);
+    r.tile_bytes = round_up(32 * L * es, 128);
+    r.tileo_bytes = round_up(32 * L * eo, 128);
+    r.off_delta = r.tile_bytes;
+    r.off_dout = 2 * r.tile_bytes;
+    r.off_bc32 = r.off_dout + r.tileo_bytes;
+    r.off_ck = r.off_bc32 + round_up(2 * r.Lp * 4, 128);
+    r.off_bar = r.off_ck + r.nblk * 128;
+    r.smem_bytes = r.off_bar + 128;
+    const int per_sm = (227 * 1024) / (r.smem_bytes + 1024);
+    if (per_sm < 3) return false;                               // too few resident warps to hide the dependent chains
+    r.u = p.u; r.delta = p.delta; r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.dout = p.dout;
+    r.du = p.du; r.ddelta = p.ddelta;
+    r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride;
+    grid = di.sms * (per_sm > 8 ? 8 : per_sm);
     if (grid > r.n_items) grid = r.n_items;
     return true;
 }
@@ -452,18 +491,31 @@ int mia_selective_scan_bwd(const mia_ss_params *pp, void *cuda_stream) {
         MIA_CUDA(cudaMemsetAsync(a.acc_dC, 0, w.acc_bytes, stream));
         g_launches.fetch_add(2);
     }
-    const int grid = a.n_seg < di.sms ? a.n_seg : di.sms;
-    int rc = dispatch(p.itype, [&](auto *tag) {
-        using T = typename std::remove_pointer<decltype(tag)>::type;
-        return (int)mia::launch_bwd_any<T>(a, grid, stream);
-    });
+    int rc = 0, bc_parts = pl.split;
+    mia::RowsBwdArgs rb;
+    int rgrid = 0;
+    if (plan_rows_bwd(p, di, rb, rgrid)) {
+        rb.part_dA = a.part_dA; rb.part_dD = a.part_dD; rb.part_dbias = a.part_dbias; rb.acc_dB = a.acc_dB; rb.acc_dC = a.acc_dC;
+        bc_parts = rb.rows_per_group / 32;
+        const bool of32 = p.otype == MIA_F32 && p.itype != MIA_F32;
+        rc = dispatch(p.itype, [&](auto *tag) {
+            using T = typename std::remove_pointer<decltype(tag)>::type;
+            return (int)mia::launch_bwd_rows<T>(rb, rgrid, of32, stream);
+        });
+    } else {
+        const int grid = a.n_seg < di.sms ? a.n_seg : di.sms;
+        rc = dispatch(p.itype, [&](auto *tag) {
+            using T = typename std::remove_pointer<decltype(tag)>::type;
+            return (int)mia::launch_bwd_any<T>(a, grid, stream);
+        });
+    }
     if (rc != 0) return fail(MIA_ECUDA, "selective_scan_bwd launch: %s", cudaGetErrorString((cudaError_t)rc));
     g_launches.fetch_add(1);
 
     FinArgs f;
     memset(&f, 0, sizeof(f));
     f.batch = p.batch; f.dim = p.dim; f.L = p.seqlen; f.N = p.dstate; f.G = p.n_groups; f.delta_dim = p.delta_dim;
-    f.ratio = p.dim / p.delta_dim; f.tiles = pl.split; f.bc_atomic = w.bc_atomic; f.Lp = (p.seqlen + 3) & ~3;
+    f.ratio = p.dim / p.delta_dim; f.tiles = bc_parts; f.bc_atomic = w.bc_atomic; f.Lp = (p.seqlen + 3) & ~3;
     f.part_dA = a.part_dA; f.part_dD = a.part_dD; f.part_dbias = a.part_dbias; f.acc_dB = a.acc_dB; f.acc_dC = a.acc_dC;
     f.ddelta_full = a.ddelta_full;
     f.dA = p.dA; f.dD = p.dD; f.dbias = p.ddelta_bias; f.dB = p.dB; f.dC = p.dC; f.ddelta = p.ddelta;

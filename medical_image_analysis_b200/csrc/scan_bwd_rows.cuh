@@ -1,0 +1,269 @@
+// Backward selective scan, ROW-SERIAL path (d_state == 1, rows of at most one 256-token chunk): one LANE per row.
+//
+// A warp owns 32 consecutive rows of one (batch, group): lane r walks the tokens of row r serially, so the scan itself
+// costs one FMA per token (no shuffle scans, no idle lanes past the row end) and B[t], C[t] are shared-memory
+// broadcasts.  The backward needs h_{t-1} while walking the row from its end, without room for a whole row of fp32
+// states per lane.  Two-level recompute:
+//   phase 1  forward over the row, keeping only the state at every 16-token block boundary (32 x 4 B per block);
+//   phase 2  blocks from last to first: recompute the block's 16 (a, h, ...) into registers from its checkpoint, then
+//            run the suffix recurrence G_t = a_t (dy_t C_t + G_{t+1}) backwards through it.
+// du / ddelta overwrite the u / delta tiles in shared memory and leave with one bulk store each (coalesced although
+// every lane produces a different row).  dA, dD, ddelta_bias are plain per-lane sums.  dB[t], dC[t] are sums over the
+// ROWS, i.e. over the lanes: the 32 per-lane values of a block (16 dB + 16 dC) go through a 31-exchange transposing
+// butterfly that leaves lane i with the warp total of value i; the per-warp partials are folded in fixed order by
+// ss_finalize_kernel (bit-reproducible, like the warp-scan path).
+//
+// Log2-domain algebra as in scan_bwd_fast.cuh: m = softplus(delta + bias) log2e, a = 2^(m A), B' = B ln2.
+// Preconditions (host-checked, otherwise the warp-scan kernels run): d_state == 1, delta per row, no z, L <= 256,
+// L % 4 == 0, rows_per_group % 32 == 0, dense 16-byte aligned u / delta / dout / du / ddelta.
+#pragma once
+#include <type_traits>
+
+#include "scan_fwd_rows.cuh"
+
+namespace mia {
+
+constexpr int kBlk = 16;   // tokens per recompute block (= values per quantity entering the butterfly)
+
+struct RowsBwdArgs {
+    int batch, dim, L, G, rows_per_group;
+    int softplus;
+    int n_items, nblk;
+    int tile_bytes, tileo_bytes;            // one [32 x L] tile of u / delta, of dout
+    int off_delta, off_dout, off_bc32, off_ck, off_bar, smem_bytes;
+    int Lp;                                 // L rounded up to kBlk (length of the fp32 B' and C rows)
+    const void *u, *delta, *A, *B, *C, *D, *delta_bias, *dout;
+    void *du, *ddelta;
+    float *part_dA, *part_dD, *part_dbias, *acc_dB, *acc_dC;
+    long long B_bs, B_gs, C_bs, C_gs;
+};
+
+__device__ __forceinline__ float2 ex2_2(float2 v) { return make_float2(ex2f(v.x), ex2f(v.y)); }
+
+// State of one 16-token block of one row, all in registers (indices are compile-time after unrolling).
+struct BlkRegs {
+    float2 a[8], h[8], e[8], r[8], w[8], f[8], u[8];
+};
+
+// Recompute the forward quantities of quad `q` (4 tokens starting at byte offsets pu/pd, fp32 B' at Bq) of a block.
+template <typename T, bool kSoftplus>
+__device__ __forceinline__ void recompute_quad(BlkRegs &R, int q, const char *pu, const char *pd, const float *Bq, float &h,
+                                               const float2 bl2, const float2 A2, const float2 Aln2) {
+    const float2 kL2E = splat2(kLog2e), kOne = splat2(1.f), kLN2 = splat2(kLn2);
+    float2 dd[2], uu[2], Bv[2];
+    Quad<T>::ld(pd, dd);
+    Quad<T>::ld(pu, uu);
+    Quad<float>::ld(reinterpret_cast<const char *>(Bq), Bv);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int k = 2 * q + p;
+        float2 m = fma2(dd[p], kL2E, bl2);                      // (delta + bias) log2e
+        float2 sg = kL2E;
+        if (kSoftplus) {
+            const float2 e = make_float2(ex2f(fminf(m.x, 120.f)), ex2f(fminf(m.y, 120.f)));
+            const float2 s = add2(e, kOne);
+            const float2 sl = fma2(e, kLN2, kLN2);              // (1 + e) ln2
+            sg = mul2(e, make_float2(rcpf(sl.x), rcpf(sl.y)));  // sigmoid log2e
+            m = make_float2(fmaxf(lg2f(s.x), m.x), fmaxf(lg2f(s.y), m.y));
+        }
+        const float2 av = ex2_2(mul2(m, A2));
+        const float2 mu = mul2(m, uu[p]);
+        const float2 bv = mul2(mu, Bv[p]);
+        float2 hp, hh;
+        hp.x = av.x * h; h = fmaf(av.x, h, bv.x); hh.x = h;     // a_t h_{t-1}, then h_t
+        hp.y = av.y * h; h = fmaf(av.y, h, bv.y); hh.y = h;
+        const float2 qv = fma2(hp, Aln2, mul2(uu[p], Bv[p]));   // ln2 d h_t / d dl_t
+        R.a[k] = av; R.h[k] = hh; R.e[k] = mu; R.u[k] = uu[p];
+        R.r[k] = mul2(qv, sg);
+        R.w[k] = mul2(m, hp);
+        R.f[k] = mul2(m, Bv[p]);
+    }
+}
+
+// One 16-token block of one 32-row batch: recompute from the checkpoint, suffix recurrence, stores, dB/dC butterfly.
+template <typename T, typename TO, bool kSoftplus, bool kFull>
+__device__ __forceinline__ void bwd_block(const int j, const int nq_in, const int L, const int lane, char *pu, char *pd, const char *po,
+                                          const float *Bf, const float *Cf, const float *ck, float *accB, float *accC,
+                                          const float2 bl2, const float2 A2, const float2 Aln2, const float2 D2,
+                                          float &G, float2 &dA2, float2 &dD2, float2 &db2) {
+    constexpr int es = (int)sizeof(T), eo = (int)sizeof(TO);
+    const int t0 = j * kBlk;
+    const int nq = kFull ? 4 : nq_in;
+    BlkRegs R;
+    float v[32];                                 // v[i] = dB term of token t0 + i, v[16 + i] = dC term
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    float h = j > 0 ? ck[j * 32] : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (kFull || q < nq) recompute_quad<T, kSoftplus>(R, q, pu + (t0 + 4 * q) * es, pd + (t0 + 4 * q) * es, Bf + t0 + 4 * q, h, bl2, A2, Aln2);
+#pragma unroll
+    for (int q = 3; q >= 0; --q) {
+        if (kFull || q < nq) {
+            const int t = t0 + 4 * q;
+            float2 dy[2], Cv[2], du[2], dd[2];
+            Quad<TO>::ld(po + t * eo, dy);
+            Quad<float>::ld(reinterpret_cast<const char *>(Cf + t), Cv);
+#pragma unroll
+            for (int p = 1; p >= 0; --p) {
+                const int k = 2 * q + p;
+                const float2 pc = mul2(dy[p], Cv[p]);
+                const float2 ap = mul2(R.a[k], pc);
+                float2 gg;
+                gg.y = pc.y + G; G = fmaf(R.a[k].y, G, ap.y);
+                gg.x = pc.x + G; G = fmaf(R.a[k].x, G, ap.x);
+                const float2 dBv = mul2(gg, R.e[k]), dCv = mul2(dy[p], R.h[k]);
+                v[2 * k] = dBv.x; v[2 * k + 1] = dBv.y;
+                v[16 + 2 * k] = dCv.x; v[17 + 2 * k] = dCv.y;
+                du[p] = fma2(gg, R.f[k], mul2(dy[p], D2));
+                dd[p] = mul2(gg, R.r[k]);
+                db2 = add2(db2, dd[p]);
+                dA2 = fma2(gg, R.w[k], dA2);
+                dD2 = fma2(dy[p], R.u[k], dD2);
+            }
+            Quad<T>::st(pu + t * es, du);        // du replaces u, ddelta replaces delta
+            Quad<T>::st(pd + t * es, dd);
+        }
+    }
+    // transposing butterfly: after the step with stride s a lane keeps the half of its values whose index has
+    // bit s equal to its own lane bit, summed with the partner's copy -> lane i ends with the warp total of v[i]
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float send = up ? v[i] : v[i + s];
+            const float keep = up ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    const int tt = t0 + (lane & 15);
+    if (kFull || tt < L) {
+        if (lane < 16) accB[tt] = v[0] * kLn2; else accC[tt] = v[0];
+    }
+}
+
+template <typename T, bool kSoftplus, bool kOutF32>
+__global__ void __launch_bounds__(32) ss_bwd_rows_kernel(const __grid_constant__ RowsBwdArgs a) {
+    extern __shared__ __align__(128) char smem[];
+    constexpr int es = (int)sizeof(T);
+    constexpr int eo = kOutF32 ? 4 : es;
+    using TO = typename std::conditional<kOutF32, float, T>::type;
+    const int lane = threadIdx.x;
+    char *tu = smem, *td = smem + a.off_delta, *to = smem + a.off_dout;
+    float *Bf = reinterpret_cast<float *>(smem + a.off_bc32), *Cf = Bf + a.Lp;
+    float *ck = reinterpret_cast<float *>(smem + a.off_ck) + lane;       // ck[j * 32]: state entering block j
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + a.off_bar);
+    if (lane == 0) { mbar_init(full, 1); fence_mbar_init(); }
+    __syncwarp();
+
+    const int L = a.L, nblk = a.nblk;
+    const int batches_per_group = a.rows_per_group / 32;
+    const float *Ap = reinterpret_cast<const float *>(a.A);
+    const float *Dp = reinterpret_cast<const float *>(a.D);
+    const float *biasp = reinterpret_cast<const float *>(a.delta_bias);
+    const float2 kL2E = splat2(kLog2e), kOne = splat2(1.f);
+    char *pu = tu + (size_t)lane * L * es;
+    char *pd = td + (size_t)lane * L * es;
+    const char *po = to + (size_t)lane * L * eo;
+    const int nq_last = (L - (nblk - 1) * kBlk) / 4;                     // quads of the (possibly ragged) last block
+    uint32_t phase = 0;
+
+    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+        const int bt = item % batches_per_group;
+        const int bg = item / batches_per_group;
+        const int g = bg % a.G, b = bg / a.G;
+        const int row0 = g * a.rows_per_group + bt * 32;
+        const int d = row0 + lane;
+        const size_t goff = ((size_t)b * a.dim + row0) * L;
+        if (lane == 0) {
+            bulk_g2s(tu, (const char *)a.u + goff * es, (uint32_t)(32 * L * es), full);
+            bulk_g2s(td, (const char *)a.delta + goff * es, (uint32_t)(32 * L * es), full);
+            bulk_g2s(to, (const char *)a.dout + goff * eo, (uint32_t)(32 * L * eo), full);
+            mbar_arrive_expect_tx(full, (uint32_t)(32 * L * (2 * es + eo)));
+        }
+        {
+            const typename Cvt<T>::raw *gB = reinterpret_cast<const typename Cvt<T>::raw *>(a.B) + (size_t)b * a.B_bs + (size_t)g * a.B_gs;
+            const typename Cvt<T>::raw *gC = reinterpret_cast<const typename Cvt<T>::raw *>(a.C) + (size_t)b * a.C_bs + (size_t)g * a.C_gs;
+            for (int i = lane; i < a.Lp; i += 32) {
+                Bf[i] = i < L ? Cvt<T>::to_f(__ldg(gB + i)) * kLn2 : 0.f;
+                Cf[i] = i < L ? Cvt<T>::to_f(__ldg(gC + i)) : 0.f;
+            }
+        }
+        const float Araw = __ldg(Ap + d);
+        const float Dv = Dp ? __ldg(Dp + d) : 0.f;
+        const float2 bl2 = splat2((biasp ? __ldg(biasp + d) : 0.f) * kLog2e), A2 = splat2(Araw), Aln2 = splat2(Araw * kLn2), D2 = splat2(Dv);
+        __syncwarp();
+        mbar_wait(full, phase);
+        phase ^= 1;
+
+        // ---- phase 1: states at the block boundaries
+        {
+            float h = 0.f;
+#pragma unroll 1
+            for (int j = 0; j + 1 < nblk; ++j) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int t = j * kBlk + 4 * q;
+                    float2 dd[2], uu[2], Bv[2];
+                    Quad<T>::ld(pd + t * es, dd);
+                    Quad<T>::ld(pu + t * es, uu);
+                    Quad<float>::ld(reinterpret_cast<const char *>(Bf + t), Bv);
+#pragma unroll
+                    for (int p = 0; p < 2; ++p) {
+                        float2 m = fma2(dd[p], kL2E, bl2);
+                        if (kSoftplus) {
+                            const float2 e = make_float2(ex2f(fminf(m.x, 120.f)), ex2f(fminf(m.y, 120.f)));
+                            const float2 s = add2(e, kOne);
+                            m = make_float2(fmaxf(lg2f(s.x), m.x), fmaxf(lg2f(s.y), m.y));
+                        }
+                        const float2 av = ex2_2(mul2(m, A2));
+                        const float2 bv = mul2(mul2(m, uu[p]), Bv[p]);
+                        h = fmaf(av.x, h, bv.x);
+                        h = fmaf(av.y, h, bv.y);
+                    }
+                }
+                ck[(j + 1) * 32] = h;
+            }
+        }
+
+        // ---- phase 2: blocks from last to first
+        float G = 0.f;                                   // a_{t+1} g_{t+1}: what the suffix recurrence hands to token t
+        float2 dA2 = make_float2(0.f, 0.f), dD2 = dA2, db2 = dA2;
+        float *accB = a.acc_dB + (size_t)item * L, *accC = a.acc_dC + (size_t)item * L;
+        // the last block may be ragged (uniform guards, cold code); all the others are straight-line 16-token code the
+        // compiler can schedule across tokens (the MUFU pipe takes one warp instruction per 8 cycles: everything else
+        // has to be interleaved with it)
+        bwd_block<T, TO, kSoftplus, false>(nblk - 1, nq_last, L, lane, pu, pd, po, Bf, Cf, ck, accB, accC, bl2, A2, Aln2, D2, G, dA2, dD2, db2);
+#pragma unroll 1
+        for (int j = nblk - 2; j >= 0; --j)
+            bwd_block<T, TO, kSoftplus, true>(j, 4, L, lane, pu, pd, po, Bf, Cf, ck, accB, accC, bl2, A2, Aln2, D2, G, dA2, dD2, db2);
+        a.part_dA[(size_t)b * a.dim + d] = (dA2.x + dA2.y) * kLn2;
+        a.part_dD[(size_t)b * a.dim + d] = dD2.x + dD2.y;
+        a.part_dbias[(size_t)b * a.dim + d] = db2.x + db2.y;
+
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_s2g((char *)a.du + goff * es, tu, (uint32_t)(32 * L * es));
+            bulk_s2g((char *)a.ddelta + goff * es, td, (uint32_t)(32 * L * es));
+            bulk_commit();
+            bulk_wait_read<0>();                         // the tiles are refilled next: they must have been read out
+        }
+        __syncwarp();
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <typename T>
+cudaError_t launch_bwd_rows(const RowsBwdArgs &a, int grid, bool dout_f32, cudaStream_t stream) {
+    void (*kernel)(const RowsBwdArgs);
+    if (a.softplus) kernel = dout_f32 ? &ss_bwd_rows_kernel<T, true, true> : &ss_bwd_rows_kernel<T, true, false>;
+    else kernel = dout_f32 ? &ss_bwd_rows_kernel<T, false, true> : &ss_bwd_rows_kernel<T, false, false>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, 32, a.smem_bytes, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace mia

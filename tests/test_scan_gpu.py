@@ -88,6 +88,26 @@ def test_scan_parity_small(shape, dtype, out_float):
     _run_case(batch, dim, L, N, G, ddim, True, False, True, True, dtype, out_float)
 
 
+# Shapes the row-serial kernels take (d_state 1, delta per row, rows_per_group % 32 == 0, L % 4 == 0; the backward one
+# for L <= 256): block-boundary, ragged-last-block and single-quad cases of the 16-token recompute blocks.
+ROWS = [(2, 64, 196, 1, 2, 64), (1, 32, 4, 1, 1, 32), (2, 96, 16, 1, 3, 96), (1, 64, 20, 1, 1, 64), (2, 64, 256, 1, 2, 64),
+        (1, 32, 252, 1, 1, 32), (2, 128, 64, 1, 4, 128), (3, 32, 36, 1, 1, 32), (1, 64, 512, 1, 2, 64), (1, 32, 1000, 1, 1, 32)]
+
+
+@pytest.mark.parametrize("shape", ROWS, ids=[f"b{s[0]}d{s[1]}L{s[2]}G{s[4]}" for s in ROWS])
+@pytest.mark.parametrize("dtype,out_float", [(torch.float32, False), (torch.bfloat16, False), (torch.bfloat16, True),
+                                             (torch.float16, False)], ids=["f32", "bf16", "bf16o32", "f16"])
+def test_scan_parity_row_serial(shape, dtype, out_float):
+    batch, dim, L, N, G, ddim = shape
+    _run_case(batch, dim, L, N, G, ddim, True, False, True, True, dtype, out_float, seed=5)
+
+
+@pytest.mark.parametrize("has_D,has_bias,softplus", list(itertools.product([False, True], repeat=3)))
+def test_scan_parity_row_serial_flags(has_D, has_bias, softplus):
+    _run_case(2, 64, 196, 1, 2, 64, has_D, False, has_bias, softplus, torch.bfloat16, False, seed=6)
+    _run_case(1, 32, 52, 1, 1, 32, has_D, False, has_bias, softplus, torch.float32, False, seed=7)
+
+
 @pytest.mark.parametrize("has_D,has_z,has_bias,softplus", list(itertools.product([False, True], repeat=4)))
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 def test_scan_parity_flags(has_D, has_z, has_bias, softplus, dtype):
