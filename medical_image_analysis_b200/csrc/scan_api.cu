@@ -289,14 +289,16 @@ bool plan_rows_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsBwdArg
     r.off_dout = 2 * r.tile_bytes;
     r.off_bc32 = r.off_dout + r.tileo_bytes;
     r.off_ck = r.off_bc32 + round_up(2 * r.Lp * 4, 128);
-    r.off_bar = r.off_ck + r.nblk * 128;
+    r.off_xch = r.off_ck + 2 * r.nblk * 128;                    // ck + ckm
+    r.off_bar = r.off_xch + 5 * 128;
     r.smem_bytes = r.off_bar + 128;
-    const int per_sm = (227 * 1024) / (r.smem_bytes + 1024);
+    int per_sm = (227 * 1024) / (r.smem_bytes + 1024);
     if (per_sm < 3) return false;                               // too few resident warps to hide the dependent chains
+    if (per_sm > 5) per_sm = 5;                                 // 64 threads x 200 registers
     r.u = p.u; r.delta = p.delta; r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.dout = p.dout;
     r.du = p.du; r.ddelta = p.ddelta;
     r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride;
-    grid = di.sms * (per_sm > 8 ? 8 : per_sm);
+    grid = di.sms * per_sm;
     if (grid > r.n_items) grid = r.n_items;
     return true;
 }

@@ -30,7 +30,7 @@ struct RowsBwdArgs {
     int softplus;
     int n_items, nblk;
     int tile_bytes, tileo_bytes;            // one [32 x L] tile of u / delta, of dout
-    int off_delta, off_dout, off_bc32, off_ck, off_bar, smem_bytes;
+    int off_delta, off_dout, off_bc32, off_ck, off_xch, off_bar, smem_bytes;
     int Lp;                                 // L rounded up to kBlk (length of the fp32 B' and C rows)
     const void *u, *delta, *A, *B, *C, *D, *delta_bias, *dout;
     void *du, *ddelta;
@@ -82,8 +82,8 @@ __device__ __forceinline__ void recompute_quad(BlkRegs &R, int q, const char *pu
 
 // One 16-token block of one 32-row batch: recompute from the checkpoint, suffix recurrence, stores, dB/dC butterfly.
 template <typename T, typename TO, bool kSoftplus, bool kFull>
-__device__ __forceinline__ void bwd_block(const int j, const int nq_in, const int L, const int lane, char *pu, char *pd, const char *po,
-                                          const float *Bf, const float *Cf, const float *ck, float *accB, float *accC,
+__device__ __forceinline__ void bwd_block(const int j, const int nq_in, const int L, const int lane, const float h0, char *pu, char *pd,
+                                          const char *po, const float *Bf, const float *Cf, float *accB, float *accC,
                                           const float2 bl2, const float2 A2, const float2 Aln2, const float2 D2,
                                           float &G, float2 &dA2, float2 &dD2, float2 &db2) {
     constexpr int es = (int)sizeof(T), eo = (int)sizeof(TO);
@@ -93,7 +93,7 @@ __device__ __forceinline__ void bwd_block(const int j, const int nq_in, const in
     float v[32];                                 // v[i] = dB term of token t0 + i, v[16 + i] = dC term
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = 0.f;
-    float h = j > 0 ? ck[j * 32] : 0.f;
+    float h = h0;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
         if (kFull || q < nq) recompute_quad<T, kSoftplus>(R, q, pu + (t0 + 4 * q) * es, pd + (t0 + 4 * q) * es, Bf + t0 + 4 * q, h, bl2, A2, Aln2);
@@ -143,26 +143,98 @@ __device__ __forceinline__ void bwd_block(const int j, const int nq_in, const in
     }
 }
 
+// Phase 1 of one 16-token block: advances the local state h (and, for the second half of the row, the running sum of
+// m and Gs = sum_t (prod_{s<=t} a_s) dy_t C_t, the suffix value the half's first token hands to the first half).
+template <typename T, typename TO, bool kSoftplus, bool kSecond, bool kFull>
+__device__ __forceinline__ void phase1_block(const int t0, const int nq, const char *pu, const char *pd, const char *po, const float *Bf,
+                                             const float *Cf, const float2 bl2, const float2 A2, float &h, float2 &msum, float &P, float &Gs) {
+    constexpr int es = (int)sizeof(T), eo = (int)sizeof(TO);
+    const float2 kL2E = splat2(kLog2e), kOne = splat2(1.f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (kFull || q < nq) {
+            const int t = t0 + 4 * q;
+            float2 dd[2], uu[2], Bv[2], dy[2], Cv[2];
+            Quad<T>::ld(pd + t * es, dd);
+            Quad<T>::ld(pu + t * es, uu);
+            Quad<float>::ld(reinterpret_cast<const char *>(Bf + t), Bv);
+            if (kSecond) {
+                Quad<TO>::ld(po + t * eo, dy);
+                Quad<float>::ld(reinterpret_cast<const char *>(Cf + t), Cv);
+            }
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                float2 m = fma2(dd[p], kL2E, bl2);
+                if (kSoftplus) {
+                    const float2 e = make_float2(ex2f(fminf(m.x, 120.f)), ex2f(fminf(m.y, 120.f)));
+                    const float2 s = add2(e, kOne);
+                    m = make_float2(fmaxf(lg2f(s.x), m.x), fmaxf(lg2f(s.y), m.y));
+                }
+                const float2 av = ex2_2(mul2(m, A2));
+                const float2 bv = mul2(mul2(m, uu[p]), Bv[p]);
+                h = fmaf(av.x, h, bv.x);
+                h = fmaf(av.y, h, bv.y);
+                if (kSecond) {
+                    msum = add2(msum, m);
+                    const float2 pc = mul2(dy[p], Cv[p]);
+                    P *= av.x; Gs = fmaf(P, pc.x, Gs);
+                    P *= av.y; Gs = fmaf(P, pc.y, Gs);
+                }
+            }
+        }
+    }
+}
+
+// Phase 1 over the blocks [jb, je) of one warp's half of the row, starting from h = 0: leaves the local state (second
+// half: also the sum of m) entering every block in ck / ckm.
+template <typename T, typename TO, bool kSoftplus, bool kSecond>
+__device__ __forceinline__ void bwd_phase1(const int jb, const int je, const int nq_last, const char *pu, const char *pd, const char *po,
+                                           const float *Bf, const float *Cf, float *ck, float *ckm, const float2 bl2, const float2 A2,
+                                           float &h_out, float &Gs_out) {
+    float h = 0.f, P = 1.f, Gs = 0.f;
+    float2 msum = make_float2(0.f, 0.f);
+    const int jfull = kSecond ? je - 1 : je;             // only the row's last block (second half) may be ragged
+#pragma unroll 1
+    for (int j = jb; j < jfull; ++j) {
+        ck[j * 32] = h;
+        if (kSecond) ckm[j * 32] = msum.x + msum.y;
+        phase1_block<T, TO, kSoftplus, kSecond, true>(j * kBlk, 4, pu, pd, po, Bf, Cf, bl2, A2, h, msum, P, Gs);
+    }
+    if (kSecond) {
+        ck[jfull * 32] = h;
+        ckm[jfull * 32] = msum.x + msum.y;
+        phase1_block<T, TO, kSoftplus, true, false>(jfull * kBlk, nq_last, pu, pd, po, Bf, Cf, bl2, A2, h, msum, P, Gs);
+    }
+    h_out = h;
+    Gs_out = Gs;
+}
+
+// CTA = 2 warps sharing one [32 rows x L] tile set: warp 0 owns the first half of the blocks, warp 1 the second half
+// (twice the resident warps per byte of shared memory; the single-warp version was latency-bound at 5 warps per SM).
 template <typename T, bool kSoftplus, bool kOutF32>
-__global__ void __launch_bounds__(32) ss_bwd_rows_kernel(const __grid_constant__ RowsBwdArgs a) {
+__global__ void __launch_bounds__(64, 5) ss_bwd_rows_kernel(const __grid_constant__ RowsBwdArgs a) {
     extern __shared__ __align__(128) char smem[];
     constexpr int es = (int)sizeof(T);
     constexpr int eo = kOutF32 ? 4 : es;
     using TO = typename std::conditional<kOutF32, float, T>::type;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     char *tu = smem, *td = smem + a.off_delta, *to = smem + a.off_dout;
     float *Bf = reinterpret_cast<float *>(smem + a.off_bc32), *Cf = Bf + a.Lp;
-    float *ck = reinterpret_cast<float *>(smem + a.off_ck) + lane;       // ck[j * 32]: state entering block j
+    float *ck = reinterpret_cast<float *>(smem + a.off_ck) + lane;       // ck[j * 32]: local state entering block j
+    float *ckm = ck + a.nblk * 32;                                       // ckm[j * 32]: sum of m before block j (2nd half)
+    float *xch = reinterpret_cast<float *>(smem + a.off_xch) + lane;     // [0]: h at the end of half 0, [32]: Gs of half 1,
+                                                                         // [64..160): dA, dD, dbias partials of warp 1
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + a.off_bar);
-    if (lane == 0) { mbar_init(full, 1); fence_mbar_init(); }
-    __syncwarp();
+    if (threadIdx.x == 0) { mbar_init(full, 1); fence_mbar_init(); }
+    __syncthreads();
 
     const int L = a.L, nblk = a.nblk;
+    const int nb0 = nblk / 2;                                            // warp 0: blocks [0, nb0), warp 1: [nb0, nblk)
+    const int jb = warp == 0 ? 0 : nb0, je = warp == 0 ? nb0 : nblk;
     const int batches_per_group = a.rows_per_group / 32;
     const float *Ap = reinterpret_cast<const float *>(a.A);
     const float *Dp = reinterpret_cast<const float *>(a.D);
     const float *biasp = reinterpret_cast<const float *>(a.delta_bias);
-    const float2 kL2E = splat2(kLog2e), kOne = splat2(1.f);
     char *pu = tu + (size_t)lane * L * es;
     char *pd = td + (size_t)lane * L * es;
     const char *po = to + (size_t)lane * L * eo;
@@ -176,7 +248,7 @@ __global__ void __launch_bounds__(32) ss_bwd_rows_kernel(const __grid_constant__
         const int row0 = g * a.rows_per_group + bt * 32;
         const int d = row0 + lane;
         const size_t goff = ((size_t)b * a.dim + row0) * L;
-        if (lane == 0) {
+        if (threadIdx.x == 0) {
             bulk_g2s(tu, (const char *)a.u + goff * es, (uint32_t)(32 * L * es), full);
             bulk_g2s(td, (const char *)a.delta + goff * es, (uint32_t)(32 * L * es), full);
             bulk_g2s(to, (const char *)a.dout + goff * eo, (uint32_t)(32 * L * eo), full);
@@ -185,7 +257,7 @@ __global__ void __launch_bounds__(32) ss_bwd_rows_kernel(const __grid_constant__
         {
             const typename Cvt<T>::raw *gB = reinterpret_cast<const typename Cvt<T>::raw *>(a.B) + (size_t)b * a.B_bs + (size_t)g * a.B_gs;
             const typename Cvt<T>::raw *gC = reinterpret_cast<const typename Cvt<T>::raw *>(a.C) + (size_t)b * a.C_bs + (size_t)g * a.C_gs;
-            for (int i = lane; i < a.Lp; i += 32) {
+            for (int i = threadIdx.x; i < a.Lp; i += 64) {
                 Bf[i] = i < L ? Cvt<T>::to_f(__ldg(gB + i)) * kLn2 : 0.f;
                 Cf[i] = i < L ? Cvt<T>::to_f(__ldg(gC + i)) : 0.f;
             }
@@ -193,64 +265,54 @@ __global__ void __launch_bounds__(32) ss_bwd_rows_kernel(const __grid_constant__
         const float Araw = __ldg(Ap + d);
         const float Dv = Dp ? __ldg(Dp + d) : 0.f;
         const float2 bl2 = splat2((biasp ? __ldg(biasp + d) : 0.f) * kLog2e), A2 = splat2(Araw), Aln2 = splat2(Araw * kLn2), D2 = splat2(Dv);
-        __syncwarp();
+        __syncthreads();                                 // B', C rows complete
         mbar_wait(full, phase);
         phase ^= 1;
 
-        // ---- phase 1: states at the block boundaries
-        {
-            float h = 0.f;
-#pragma unroll 1
-            for (int j = 0; j + 1 < nblk; ++j) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int t = j * kBlk + 4 * q;
-                    float2 dd[2], uu[2], Bv[2];
-                    Quad<T>::ld(pd + t * es, dd);
-                    Quad<T>::ld(pu + t * es, uu);
-                    Quad<float>::ld(reinterpret_cast<const char *>(Bf + t), Bv);
-#pragma unroll
-                    for (int p = 0; p < 2; ++p) {
-                        float2 m = fma2(dd[p], kL2E, bl2);
-                        if (kSoftplus) {
-                            const float2 e = make_float2(ex2f(fminf(m.x, 120.f)), ex2f(fminf(m.y, 120.f)));
-                            const float2 s = add2(e, kOne);
-                            m = make_float2(fmaxf(lg2f(s.x), m.x), fmaxf(lg2f(s.y), m.y));
-                        }
-                        const float2 av = ex2_2(mul2(m, A2));
-                        const float2 bv = mul2(mul2(m, uu[p]), Bv[p]);
-                        h = fmaf(av.x, h, bv.x);
-                        h = fmaf(av.y, h, bv.y);
-                    }
-                }
-                ck[(j + 1) * 32] = h;
-            }
-        }
+        // ---- phase 1: local states at the block boundaries of this warp's half; exchange the two boundary values
+        float hend, Gs;
+        if (warp == 0) bwd_phase1<T, TO, kSoftplus, false>(jb, je, nq_last, pu, pd, po, Bf, Cf, ck, ckm, bl2, A2, hend, Gs);
+        else bwd_phase1<T, TO, kSoftplus, true>(jb, je, nq_last, pu, pd, po, Bf, Cf, ck, ckm, bl2, A2, hend, Gs);
+        xch[warp * 32] = warp == 0 ? hend : Gs;
+        __syncthreads();
+        const float other = xch[(1 - warp) * 32];
+        const float hA = warp == 0 ? 0.f : other;        // state entering the second half
+        float G = warp == 0 ? other : 0.f;               // a_{t+1} g_{t+1}: what the suffix recurrence hands to token t
 
-        // ---- phase 2: blocks from last to first
-        float G = 0.f;                                   // a_{t+1} g_{t+1}: what the suffix recurrence hands to token t
+        // ---- phase 2: this warp's blocks from last to first
         float2 dA2 = make_float2(0.f, 0.f), dD2 = dA2, db2 = dA2;
         float *accB = a.acc_dB + (size_t)item * L, *accC = a.acc_dC + (size_t)item * L;
-        // the last block may be ragged (uniform guards, cold code); all the others are straight-line 16-token code the
-        // compiler can schedule across tokens (the MUFU pipe takes one warp instruction per 8 cycles: everything else
-        // has to be interleaved with it)
-        bwd_block<T, TO, kSoftplus, false>(nblk - 1, nq_last, L, lane, pu, pd, po, Bf, Cf, ck, accB, accC, bl2, A2, Aln2, D2, G, dA2, dD2, db2);
-#pragma unroll 1
-        for (int j = nblk - 2; j >= 0; --j)
-            bwd_block<T, TO, kSoftplus, true>(j, 4, L, lane, pu, pd, po, Bf, Cf, ck, accB, accC, bl2, A2, Aln2, D2, G, dA2, dD2, db2);
-        a.part_dA[(size_t)b * a.dim + d] = (dA2.x + dA2.y) * kLn2;
-        a.part_dD[(size_t)b * a.dim + d] = dD2.x + dD2.y;
-        a.part_dbias[(size_t)b * a.dim + d] = db2.x + db2.y;
-
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-            bulk_s2g((char *)a.du + goff * es, tu, (uint32_t)(32 * L * es));
-            bulk_s2g((char *)a.ddelta + goff * es, td, (uint32_t)(32 * L * es));
-            bulk_commit();
-            bulk_wait_read<0>();                         // the tiles are refilled next: they must have been read out
+        // only the last block of the row (always in warp 1's half) may be ragged: uniform guards, cold code; all the
+        // others are straight-line 16-token code the compiler can schedule across tokens
+        int j = je - 1;
+        if (warp == 1) {
+            const float h0 = fmaf(ex2f(Araw * ckm[j * 32]), hA, ck[j * 32]);
+            bwd_block<T, TO, kSoftplus, false>(j, nq_last, L, lane, h0, pu, pd, po, Bf, Cf, accB, accC, bl2, A2, Aln2, D2, G, dA2, dD2, db2);
+            --j;
         }
-        __syncwarp();
+#pragma unroll 1
+        for (; j >= jb; --j) {
+            const float h0 = warp == 0 ? ck[j * 32] : fmaf(ex2f(Araw * ckm[j * 32]), hA, ck[j * 32]);
+            bwd_block<T, TO, kSoftplus, true>(j, 4, L, lane, h0, pu, pd, po, Bf, Cf, accB, accC, bl2, A2, Aln2, D2, G, dA2, dD2, db2);
+        }
+        if (warp == 1) {
+            xch[64] = dA2.x + dA2.y; xch[96] = dD2.x + dD2.y; xch[128] = db2.x + db2.y;
+        }
+        fence_proxy_async();                             // du / ddelta tiles: generic-proxy writes -> bulk store
+        __syncthreads();
+        if (warp == 0) {
+            a.part_dA[(size_t)b * a.dim + d] = (dA2.x + dA2.y + xch[64]) * kLn2;
+            a.part_dD[(size_t)b * a.dim + d] = dD2.x + dD2.y + xch[96];
+            a.part_dbias[(size_t)b * a.dim + d] = db2.x + db2.y + xch[128];
+            if (lane == 0) {
+                bulk_s2g((char *)a.du + goff * es, tu, (uint32_t)(32 * L * es));
+                bulk_s2g((char *)a.ddelta + goff * es, td, (uint32_t)(32 * L * es));
+                bulk_commit();
+                bulk_wait_read<0>();                     // the tiles are refilled next: they must have been read out
+            }
+        }
+        // no barrier here: warp 1 only touches B' / C rows (free since the barrier above) until the next one; the tiles
+        // are refilled by thread 0 after its wait, xch is rewritten after the next item's barriers
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -262,7 +324,7 @@ cudaError_t launch_bwd_rows(const RowsBwdArgs &a, int grid, bool dout_f32, cudaS
     else kernel = dout_f32 ? &ss_bwd_rows_kernel<T, false, true> : &ss_bwd_rows_kernel<T, false, false>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
     if (e != cudaSuccess) return e;
-    kernel<<<grid, 32, a.smem_bytes, stream>>>(a);
+    kernel<<<grid, 64, a.smem_bytes, stream>>>(a);
     return cudaGetLastError();
 }
 
