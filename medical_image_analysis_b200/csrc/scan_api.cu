@@ -280,8 +280,10 @@ bool plan_rows_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsBwdArg
     if (((uintptr_t)p.u | (uintptr_t)p.delta | (uintptr_t)p.dout | (uintptr_t)p.du | (uintptr_t)p.ddelta) & 15) return false;
     memset(&r, 0, sizeof(r));
     r.batch = p.batch; r.dim = p.dim; r.L = L; r.G = p.n_groups; r.rows_per_group = rpg; r.softplus = p.delta_softplus;
-    r.nblk = (L + mia::kBlk - 1) / mia::kBlk;
-    r.Lp = r.nblk * mia::kBlk;
+    r.T0 = (L * 13 / 25) / 4 * 4;                               // 52 % of the row to the half that has no Gs to accumulate
+    const int longer = r.T0 > L - r.T0 ? r.T0 : L - r.T0;
+    r.nblk = (longer + mia::kBlk - 1) / mia::kBlk;
+    r.Lp = (L + mia::kBlk - 1) / mia::kBlk * mia::kBlk + mia::kBlk;
     r.n_items = p.batch * p.n_groups * (rpg / 32);
     r.tile_bytes = round_up(32 * L * es, 128);
     r.tileo_bytes = round_up(32 * L * eo, 128);
@@ -289,7 +291,7 @@ bool plan_rows_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsBwdArg
     r.off_dout = 2 * r.tile_bytes;
     r.off_bc32 = r.off_dout + r.tileo_bytes;
     r.off_ck = r.off_bc32 + round_up(2 * r.Lp * 4, 128);
-    r.off_xch = r.off_ck + 2 * r.nblk * 128;                    // ck + ckm
+    r.off_xch = r.off_ck + 3 * r.nblk * 128;                    // ck of both halves + ckm
     r.off_bar = r.off_xch + 5 * 128;
     r.smem_bytes = r.off_bar + 128;
     int per_sm = (227 * 1024) / (r.smem_bytes + 1024);

@@ -17,6 +17,8 @@
 // Preconditions (host-checked, otherwise the warp-scan kernels run): d_state == 1, delta per row, no z, L <= 256,
 // L % 4 == 0, rows_per_group % 32 == 0, dense 16-byte aligned u / delta / dout / du / ddelta.
 #pragma once
+#include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
 #include "scan_fwd_rows.cuh"
@@ -28,7 +30,7 @@ constexpr int kBlk = 16;   // tokens per recompute block (= values per quantity 
 struct RowsBwdArgs {
     int batch, dim, L, G, rows_per_group;
     int softplus;
-    int n_items, nblk;
+    int n_items, nblk, T0;                 // nblk: checkpoint slots per half; T0: first token of the second half
     int tile_bytes, tileo_bytes;            // one [32 x L] tile of u / delta, of dout
     int off_delta, off_dout, off_bc32, off_ck, off_xch, off_bar, smem_bytes;
     int Lp;                                 // L rounded up to kBlk (length of the fp32 B' and C rows)
@@ -82,12 +84,11 @@ __device__ __forceinline__ void recompute_quad(BlkRegs &R, int q, const char *pu
 
 // One 16-token block of one 32-row batch: recompute from the checkpoint, suffix recurrence, stores, dB/dC butterfly.
 template <typename T, typename TO, bool kSoftplus, bool kFull>
-__device__ __forceinline__ void bwd_block(const int j, const int nq_in, const int L, const int lane, const float h0, char *pu, char *pd,
+__device__ __forceinline__ void bwd_block(const int t0, const int nq_in, const int tend, const int lane, const float h0, char *pu, char *pd,
                                           const char *po, const float *Bf, const float *Cf, float *accB, float *accC,
                                           const float2 bl2, const float2 A2, const float2 Aln2, const float2 D2,
                                           float &G, float2 &dA2, float2 &dD2, float2 &db2) {
     constexpr int es = (int)sizeof(T), eo = (int)sizeof(TO);
-    const int t0 = j * kBlk;
     const int nq = kFull ? 4 : nq_in;
     BlkRegs R;
     float v[32];                                 // v[i] = dB term of token t0 + i, v[16 + i] = dC term
@@ -138,7 +139,7 @@ __device__ __forceinline__ void bwd_block(const int j, const int nq_in, const in
         }
     }
     const int tt = t0 + (lane & 15);
-    if (kFull || tt < L) {
+    if (kFull || tt < tend) {
         if (lane < 16) accB[tt] = v[0] * kLn2; else accC[tt] = v[0];
     }
 }
@@ -185,25 +186,24 @@ __device__ __forceinline__ void phase1_block(const int t0, const int nq, const c
     }
 }
 
-// Phase 1 over the blocks [jb, je) of one warp's half of the row, starting from h = 0: leaves the local state (second
-// half: also the sum of m) entering every block in ck / ckm.
+// Phase 1 over one warp's half of the row (tokens [tb, tb + 16 (nb - 1) + 4 nq_last), nb blocks aligned to tb),
+// starting from h = 0: leaves the local state (second half: also the sum of m) entering every block in ck / ckm.
 template <typename T, typename TO, bool kSoftplus, bool kSecond>
-__device__ __forceinline__ void bwd_phase1(const int jb, const int je, const int nq_last, const char *pu, const char *pd, const char *po,
+__device__ __forceinline__ void bwd_phase1(const int tb, const int nb, const int nq_last, const char *pu, const char *pd, const char *po,
                                            const float *Bf, const float *Cf, float *ck, float *ckm, const float2 bl2, const float2 A2,
                                            float &h_out, float &Gs_out) {
     float h = 0.f, P = 1.f, Gs = 0.f;
     float2 msum = make_float2(0.f, 0.f);
-    const int jfull = kSecond ? je - 1 : je;             // only the row's last block (second half) may be ragged
 #pragma unroll 1
-    for (int j = jb; j < jfull; ++j) {
+    for (int j = 0; j < nb - 1; ++j) {
         ck[j * 32] = h;
         if (kSecond) ckm[j * 32] = msum.x + msum.y;
-        phase1_block<T, TO, kSoftplus, kSecond, true>(j * kBlk, 4, pu, pd, po, Bf, Cf, bl2, A2, h, msum, P, Gs);
+        phase1_block<T, TO, kSoftplus, kSecond, true>(tb + j * kBlk, 4, pu, pd, po, Bf, Cf, bl2, A2, h, msum, P, Gs);
     }
-    if (kSecond) {
-        ck[jfull * 32] = h;
-        ckm[jfull * 32] = msum.x + msum.y;
-        phase1_block<T, TO, kSoftplus, true, false>(jfull * kBlk, nq_last, pu, pd, po, Bf, Cf, bl2, A2, h, msum, P, Gs);
+    if (nb > 0) {                                        // the half's last block may be ragged
+        ck[(nb - 1) * 32] = h;
+        if (kSecond) ckm[(nb - 1) * 32] = msum.x + msum.y;
+        phase1_block<T, TO, kSoftplus, kSecond, false>(tb + (nb - 1) * kBlk, nq_last, pu, pd, po, Bf, Cf, bl2, A2, h, msum, P, Gs);
     }
     h_out = h;
     Gs_out = Gs;
@@ -220,17 +220,21 @@ __global__ void __launch_bounds__(64, 5) ss_bwd_rows_kernel(const __grid_constan
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     char *tu = smem, *td = smem + a.off_delta, *to = smem + a.off_dout;
     float *Bf = reinterpret_cast<float *>(smem + a.off_bc32), *Cf = Bf + a.Lp;
-    float *ck = reinterpret_cast<float *>(smem + a.off_ck) + lane;       // ck[j * 32]: local state entering block j
-    float *ckm = ck + a.nblk * 32;                                       // ckm[j * 32]: sum of m before block j (2nd half)
+    float *ck = reinterpret_cast<float *>(smem + a.off_ck) + (warp * a.nblk) * 32 + lane;   // ck[j * 32]: local state entering
+                                                                                            // block j of this warp's half
+    float *ckm = reinterpret_cast<float *>(smem + a.off_ck) + 2 * a.nblk * 32 + lane;       // sum of m before block j (2nd half)
     float *xch = reinterpret_cast<float *>(smem + a.off_xch) + lane;     // [0]: h at the end of half 0, [32]: Gs of half 1,
                                                                          // [64..160): dA, dD, dbias partials of warp 1
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + a.off_bar);
     if (threadIdx.x == 0) { mbar_init(full, 1); fence_mbar_init(); }
     __syncthreads();
 
-    const int L = a.L, nblk = a.nblk;
-    const int nb0 = nblk / 2;                                            // warp 0: blocks [0, nb0), warp 1: [nb0, nblk)
-    const int jb = warp == 0 ? 0 : nb0, je = warp == 0 ? nb0 : nblk;
+    // warp 0 owns tokens [0, T0), warp 1 [T0, L); blocks are aligned to the start of each half, so each half ends with
+    // its own (possibly ragged) block.  The second half also accumulates Gs in phase 1: it gets slightly fewer tokens.
+    const int L = a.L, T0 = a.T0;
+    const int tb = warp == 0 ? 0 : T0, tn = warp == 0 ? T0 : L - T0, tend = tb + tn;
+    const int nb = (tn + kBlk - 1) / kBlk;
+    const int nq_last = (tn - (nb - 1) * kBlk) / 4;                      // quads of the half's last block
     const int batches_per_group = a.rows_per_group / 32;
     const float *Ap = reinterpret_cast<const float *>(a.A);
     const float *Dp = reinterpret_cast<const float *>(a.D);
@@ -238,7 +242,6 @@ __global__ void __launch_bounds__(64, 5) ss_bwd_rows_kernel(const __grid_constan
     char *pu = tu + (size_t)lane * L * es;
     char *pd = td + (size_t)lane * L * es;
     const char *po = to + (size_t)lane * L * eo;
-    const int nq_last = (L - (nblk - 1) * kBlk) / 4;                     // quads of the (possibly ragged) last block
     uint32_t phase = 0;
 
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
@@ -271,8 +274,8 @@ __global__ void __launch_bounds__(64, 5) ss_bwd_rows_kernel(const __grid_constan
 
         // ---- phase 1: local states at the block boundaries of this warp's half; exchange the two boundary values
         float hend, Gs;
-        if (warp == 0) bwd_phase1<T, TO, kSoftplus, false>(jb, je, nq_last, pu, pd, po, Bf, Cf, ck, ckm, bl2, A2, hend, Gs);
-        else bwd_phase1<T, TO, kSoftplus, true>(jb, je, nq_last, pu, pd, po, Bf, Cf, ck, ckm, bl2, A2, hend, Gs);
+        if (warp == 0) bwd_phase1<T, TO, kSoftplus, false>(tb, nb, nq_last, pu, pd, po, Bf, Cf, ck, ckm, bl2, A2, hend, Gs);
+        else bwd_phase1<T, TO, kSoftplus, true>(tb, nb, nq_last, pu, pd, po, Bf, Cf, ck, ckm, bl2, A2, hend, Gs);
         xch[warp * 32] = warp == 0 ? hend : Gs;
         __syncthreads();
         const float other = xch[(1 - warp) * 32];
@@ -282,18 +285,18 @@ __global__ void __launch_bounds__(64, 5) ss_bwd_rows_kernel(const __grid_constan
         // ---- phase 2: this warp's blocks from last to first
         float2 dA2 = make_float2(0.f, 0.f), dD2 = dA2, db2 = dA2;
         float *accB = a.acc_dB + (size_t)item * L, *accC = a.acc_dC + (size_t)item * L;
-        // only the last block of the row (always in warp 1's half) may be ragged: uniform guards, cold code; all the
-        // others are straight-line 16-token code the compiler can schedule across tokens
-        int j = je - 1;
-        if (warp == 1) {
-            const float h0 = fmaf(ex2f(Araw * ckm[j * 32]), hA, ck[j * 32]);
-            bwd_block<T, TO, kSoftplus, false>(j, nq_last, L, lane, h0, pu, pd, po, Bf, Cf, accB, accC, bl2, A2, Aln2, D2, G, dA2, dD2, db2);
+        // only the last block of a half may be ragged: uniform guards, cold code; all the others are straight-line
+        // 16-token code the compiler can schedule across tokens
+        int j = nb - 1;
+        if (nb > 0 && nq_last < 4) {
+            const float h0 = warp == 0 ? ck[j * 32] : fmaf(ex2f(Araw * ckm[j * 32]), hA, ck[j * 32]);
+            bwd_block<T, TO, kSoftplus, false>(tb + j * kBlk, nq_last, tend, lane, h0, pu, pd, po, Bf, Cf, accB, accC, bl2, A2, Aln2, D2, G, dA2, dD2, db2);
             --j;
         }
 #pragma unroll 1
-        for (; j >= jb; --j) {
+        for (; j >= 0; --j) {
             const float h0 = warp == 0 ? ck[j * 32] : fmaf(ex2f(Araw * ckm[j * 32]), hA, ck[j * 32]);
-            bwd_block<T, TO, kSoftplus, true>(j, 4, L, lane, h0, pu, pd, po, Bf, Cf, accB, accC, bl2, A2, Aln2, D2, G, dA2, dD2, db2);
+            bwd_block<T, TO, kSoftplus, true>(tb + j * kBlk, 4, tend, lane, h0, pu, pd, po, Bf, Cf, accB, accC, bl2, A2, Aln2, D2, G, dA2, dD2, db2);
         }
         if (warp == 1) {
             xch[64] = dA2.x + dA2.y; xch[96] = dD2.x + dD2.y; xch[128] = db2.x + db2.y;
@@ -324,6 +327,11 @@ cudaError_t launch_bwd_rows(const RowsBwdArgs &a, int grid, bool dout_f32, cudaS
     else kernel = dout_f32 ? &ss_bwd_rows_kernel<T, false, true> : &ss_bwd_rows_kernel<T, false, false>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
     if (e != cudaSuccess) return e;
+    if (getenv("MIA_DEBUG")) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 64, a.smem_bytes);
+        fprintf(stderr, "[mia] ss_bwd_rows: grid %d, smem %d B, resident CTAs/SM %d\n", grid, a.smem_bytes, nb);
+    }
     kernel<<<grid, 64, a.smem_bytes, stream>>>(a);
     return cudaGetLastError();
 }
