@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/mia_selective_scan.h"
@@ -237,6 +238,7 @@ bool plan_rows_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsArgs &
     const int es = esize(p.itype), L = p.seqlen;
     const int rpg = p.dim / p.n_groups;
     if (p.dstate != 1 || p.z || p.delta_dim != p.dim || (rpg % 32) || (L % 4)) return false;
+    if (getenv("MIA_NO_ROWS_FWD")) return false;                // debugging knob: force the warp-scan kernels
     auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
     if (!dense(p.u_batch_stride, p.u_d_stride) || !dense(p.delta_batch_stride, p.delta_d_stride) ||
         !dense(p.out_batch_stride, p.out_d_stride)) return false;
@@ -271,7 +273,12 @@ bool plan_rows_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsArgs &
 bool plan_rows_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsBwdArgs &r, int &grid) {
     const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
     const int rpg = p.dim / p.n_groups;
-    if (p.dstate != 1 || p.z || p.delta_dim != p.dim || (rpg % 32) || (L % 4) || L > 256) return false;
+    if (p.dstate != 1 || p.z || p.delta_dim != p.dim || (rpg % 32) || (L % 4)) return false;
+    if (getenv("MIA_NO_ROWS_BWD")) return false;                // debugging knob: force the warp-scan kernels
+    const int CH = mia::kRowsChunk;
+    const int nch = (L + CH - 1) / CH;
+    // long rows: x must hold a checkpoint every 256 tokens, and the per-row pieces of a tile must be 16-byte aligned
+    if (nch > 1 && (mia_ss_chunk_len(L) != CH || !p.x || ((L * es) % 16) || ((L * eo) % 16))) return false;
     auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
     if (!dense(p.u_batch_stride, p.u_d_stride) || !dense(p.delta_batch_stride, p.delta_d_stride) ||
         !dense(p.dout_batch_stride, p.dout_d_stride) || !dense(p.du_batch_stride, p.du_d_stride) ||
@@ -280,27 +287,33 @@ bool plan_rows_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsBwdArg
     if (((uintptr_t)p.u | (uintptr_t)p.delta | (uintptr_t)p.dout | (uintptr_t)p.du | (uintptr_t)p.ddelta) & 15) return false;
     memset(&r, 0, sizeof(r));
     r.batch = p.batch; r.dim = p.dim; r.L = L; r.G = p.n_groups; r.rows_per_group = rpg; r.softplus = p.delta_softplus;
-    r.T0 = (L * 13 / 25) / 4 * 4;                               // 52 % of the row to the half that has no Gs to accumulate
-    const int longer = r.T0 > L - r.T0 ? r.T0 : L - r.T0;
+    r.n_chunks = nch;
+    const int span = nch == 1 ? L : CH;                         // tokens of a row resident at a time
+    const int T0 = (span * 13 / 25) / 4 * 4;                    // 52 % of the chunk to the half that has no Gs to accumulate
+    const int longer = T0 > span - T0 ? T0 : span - T0;
     r.nblk = (longer + mia::kBlk - 1) / mia::kBlk;
-    r.Lp = (L + mia::kBlk - 1) / mia::kBlk * mia::kBlk + mia::kBlk;
+    r.Lp = (span + mia::kBlk - 1) / mia::kBlk * mia::kBlk + mia::kBlk;
     r.n_items = p.batch * p.n_groups * (rpg / 32);
-    r.tile_bytes = round_up(32 * L * es, 128);
-    r.tileo_bytes = round_up(32 * L * eo, 128);
+    r.tile_bytes = round_up(32 * (span * es + (nch > 1 ? 16 : 0)), 128);
+    r.tileo_bytes = round_up(32 * (span * eo + (nch > 1 ? 16 : 0)), 128);
     r.off_delta = r.tile_bytes;
     r.off_dout = 2 * r.tile_bytes;
     r.off_bc32 = r.off_dout + r.tileo_bytes;
     r.off_ck = r.off_bc32 + round_up(2 * r.Lp * 4, 128);
     r.off_xch = r.off_ck + 3 * r.nblk * 128;                    // ck of both halves + ckm
-    r.off_bar = r.off_xch + 5 * 128;
+    r.off_bar = r.off_xch + 7 * 128;
     r.smem_bytes = r.off_bar + 128;
     int per_sm = (227 * 1024) / (r.smem_bytes + 1024);
     if (per_sm < 3) return false;                               // too few resident warps to hide the dependent chains
-    if (per_sm > 5) per_sm = 5;                                 // 64 threads x 200 registers
+    if (per_sm > 5) per_sm = 5;                                 // 64 threads x 168 registers: 3 warps per scheduler
     r.u = p.u; r.delta = p.delta; r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.dout = p.dout;
-    r.du = p.du; r.ddelta = p.ddelta;
+    r.du = p.du; r.ddelta = p.ddelta; r.x = p.x;
     r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride;
     grid = di.sms * per_sm;
+    // Long rows: a CTA walks its 32 rows chunk by chunk and each chunk is latency-bound (load -> phase 1 -> exchange ->
+    // phase 2 -> store), so this path only wins while every item gets its own resident CTA (measured on B200, L = 6400:
+    // 546 vs 734 us at 0.65 items per slot, 1076 vs 1123 us at 1.3, 2017 vs 1769 us at 2.6).
+    if (nch > 1 && r.n_items > grid) return false;
     if (grid > r.n_items) grid = r.n_items;
     return true;
 }

@@ -26,15 +26,17 @@
 namespace mia {
 
 constexpr int kBlk = 16;   // tokens per recompute block (= values per quantity entering the butterfly)
+constexpr int kRowsChunk = 256;   // tokens per staged chunk of a long row = checkpoint spacing of x (kTok * 32)
 
 struct RowsBwdArgs {
     int batch, dim, L, G, rows_per_group;
     int softplus;
-    int n_items, nblk, T0;                 // nblk: checkpoint slots per half; T0: first token of the second half
+    int n_items, nblk, n_chunks;           // nblk: checkpoint slots per half of a chunk; n_chunks: 256-token chunks per row
     int tile_bytes, tileo_bytes;            // one [32 x L] tile of u / delta, of dout
     int off_delta, off_dout, off_bc32, off_ck, off_xch, off_bar, smem_bytes;
     int Lp;                                 // L rounded up to kBlk (length of the fp32 B' and C rows)
     const void *u, *delta, *A, *B, *C, *D, *delta_bias, *dout;
+    const float *x;                         // forward checkpoints (batch, dim, n_chunks, 2), read when n_chunks > 1
     void *du, *ddelta;
     float *part_dA, *part_dD, *part_dbias, *acc_dB, *acc_dC;
     long long B_bs, B_gs, C_bs, C_gs;
@@ -187,12 +189,12 @@ __device__ __forceinline__ void phase1_block(const int t0, const int nq, const c
 }
 
 // Phase 1 over one warp's half of the row (tokens [tb, tb + 16 (nb - 1) + 4 nq_last), nb blocks aligned to tb),
-// starting from h = 0: leaves the local state (second half: also the sum of m) entering every block in ck / ckm.
+// starting from h_in (second half: 0): leaves the local state (second half: also the sum of m) entering every block in ck / ckm.
 template <typename T, typename TO, bool kSoftplus, bool kSecond>
 __device__ __forceinline__ void bwd_phase1(const int tb, const int nb, const int nq_last, const char *pu, const char *pd, const char *po,
                                            const float *Bf, const float *Cf, float *ck, float *ckm, const float2 bl2, const float2 A2,
-                                           float &h_out, float &Gs_out) {
-    float h = 0.f, P = 1.f, Gs = 0.f;
+                                           const float h_in, float &h_out, float &Gs_out, float &P_out) {
+    float h = h_in, P = 1.f, Gs = 0.f;
     float2 msum = make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int j = 0; j < nb - 1; ++j) {
@@ -207,6 +209,7 @@ __device__ __forceinline__ void bwd_phase1(const int tb, const int nb, const int
     }
     h_out = h;
     Gs_out = Gs;
+    P_out = P;
 }
 
 // CTA = 2 warps sharing one [32 rows x L] tile set: warp 0 owns the first half of the blocks, warp 1 the second half
@@ -223,25 +226,28 @@ __global__ void __launch_bounds__(64, 5) ss_bwd_rows_kernel(const __grid_constan
     float *ck = reinterpret_cast<float *>(smem + a.off_ck) + (warp * a.nblk) * 32 + lane;   // ck[j * 32]: local state entering
                                                                                             // block j of this warp's half
     float *ckm = reinterpret_cast<float *>(smem + a.off_ck) + 2 * a.nblk * 32 + lane;       // sum of m before block j (2nd half)
-    float *xch = reinterpret_cast<float *>(smem + a.off_xch) + lane;     // [0]: h at the end of half 0, [32]: Gs of half 1,
-                                                                         // [64..160): dA, dD, dbias partials of warp 1
+    float *xch = reinterpret_cast<float *>(smem + a.off_xch) + lane;     // [0]: h at the end of half 0, [32]: G entering half 0,
+                                                                         // [64..160): dA, dD, dbias partials of warp 1,
+                                                                         // [160..224): G entering a chunk (by chunk parity)
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + a.off_bar);
     if (threadIdx.x == 0) { mbar_init(full, 1); fence_mbar_init(); }
     __syncthreads();
 
-    // warp 0 owns tokens [0, T0), warp 1 [T0, L); blocks are aligned to the start of each half, so each half ends with
-    // its own (possibly ragged) block.  The second half also accumulates Gs in phase 1: it gets slightly fewer tokens.
-    const int L = a.L, T0 = a.T0;
-    const int tb = warp == 0 ? 0 : T0, tn = warp == 0 ? T0 : L - T0, tend = tb + tn;
-    const int nb = (tn + kBlk - 1) / kBlk;
-    const int nq_last = (tn - (nb - 1) * kBlk) / 4;                      // quads of the half's last block
+    // Rows longer than one 256-token chunk are walked chunk by chunk from the last to the first, the state entering a
+    // chunk coming from the forward's checkpoints x and the suffix value G being carried from chunk to chunk.  Within
+    // a chunk warp 0 owns tokens [0, T0), warp 1 [T0, len); blocks are aligned to the start of each half, so each half
+    // ends with its own (possibly ragged) block.  The second half also accumulates Gs in phase 1: it gets ~48 %.
+    const int L = a.L, nch = a.n_chunks;
     const int batches_per_group = a.rows_per_group / 32;
     const float *Ap = reinterpret_cast<const float *>(a.A);
     const float *Dp = reinterpret_cast<const float *>(a.D);
     const float *biasp = reinterpret_cast<const float *>(a.delta_bias);
-    char *pu = tu + (size_t)lane * L * es;
-    char *pd = td + (size_t)lane * L * es;
-    const char *po = to + (size_t)lane * L * eo;
+    // bytes between two rows of a tile: the row itself when the whole [32 x L] tile is one flat copy; one chunk + 16 B
+    // for per-row pieces (a 512-byte pitch would put all 32 lanes on the same banks)
+    const int pitch = nch == 1 ? L * es : kRowsChunk * es + 16, pitcho = nch == 1 ? L * eo : kRowsChunk * eo + 16;
+    char *pu = tu + (size_t)lane * pitch;
+    char *pd = td + (size_t)lane * pitch;
+    const char *po = to + (size_t)lane * pitcho;
     uint32_t phase = 0;
 
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
@@ -250,72 +256,109 @@ __global__ void __launch_bounds__(64, 5) ss_bwd_rows_kernel(const __grid_constan
         const int g = bg % a.G, b = bg / a.G;
         const int row0 = g * a.rows_per_group + bt * 32;
         const int d = row0 + lane;
-        const size_t goff = ((size_t)b * a.dim + row0) * L;
-        if (threadIdx.x == 0) {
-            bulk_g2s(tu, (const char *)a.u + goff * es, (uint32_t)(32 * L * es), full);
-            bulk_g2s(td, (const char *)a.delta + goff * es, (uint32_t)(32 * L * es), full);
-            bulk_g2s(to, (const char *)a.dout + goff * eo, (uint32_t)(32 * L * eo), full);
-            mbar_arrive_expect_tx(full, (uint32_t)(32 * L * (2 * es + eo)));
-        }
-        {
-            const typename Cvt<T>::raw *gB = reinterpret_cast<const typename Cvt<T>::raw *>(a.B) + (size_t)b * a.B_bs + (size_t)g * a.B_gs;
-            const typename Cvt<T>::raw *gC = reinterpret_cast<const typename Cvt<T>::raw *>(a.C) + (size_t)b * a.C_bs + (size_t)g * a.C_gs;
-            for (int i = threadIdx.x; i < a.Lp; i += 64) {
-                Bf[i] = i < L ? Cvt<T>::to_f(__ldg(gB + i)) * kLn2 : 0.f;
-                Cf[i] = i < L ? Cvt<T>::to_f(__ldg(gC + i)) : 0.f;
-            }
-        }
         const float Araw = __ldg(Ap + d);
         const float Dv = Dp ? __ldg(Dp + d) : 0.f;
         const float2 bl2 = splat2((biasp ? __ldg(biasp + d) : 0.f) * kLog2e), A2 = splat2(Araw), Aln2 = splat2(Araw * kLn2), D2 = splat2(Dv);
-        __syncthreads();                                 // B', C rows complete
-        mbar_wait(full, phase);
-        phase ^= 1;
-
-        // ---- phase 1: local states at the block boundaries of this warp's half; exchange the two boundary values
-        float hend, Gs;
-        if (warp == 0) bwd_phase1<T, TO, kSoftplus, false>(tb, nb, nq_last, pu, pd, po, Bf, Cf, ck, ckm, bl2, A2, hend, Gs);
-        else bwd_phase1<T, TO, kSoftplus, true>(tb, nb, nq_last, pu, pd, po, Bf, Cf, ck, ckm, bl2, A2, hend, Gs);
-        xch[warp * 32] = warp == 0 ? hend : Gs;
-        __syncthreads();
-        const float other = xch[(1 - warp) * 32];
-        const float hA = warp == 0 ? 0.f : other;        // state entering the second half
-        float G = warp == 0 ? other : 0.f;               // a_{t+1} g_{t+1}: what the suffix recurrence hands to token t
-
-        // ---- phase 2: this warp's blocks from last to first
+        const float2 *xrow = reinterpret_cast<const float2 *>(a.x) + ((size_t)b * a.dim + d) * nch;
         float2 dA2 = make_float2(0.f, 0.f), dD2 = dA2, db2 = dA2;
-        float *accB = a.acc_dB + (size_t)item * L, *accC = a.acc_dC + (size_t)item * L;
-        // only the last block of a half may be ragged: uniform guards, cold code; all the others are straight-line
-        // 16-token code the compiler can schedule across tokens
-        int j = nb - 1;
-        if (nb > 0 && nq_last < 4) {
-            const float h0 = warp == 0 ? ck[j * 32] : fmaf(ex2f(Araw * ckm[j * 32]), hA, ck[j * 32]);
-            bwd_block<T, TO, kSoftplus, false>(tb + j * kBlk, nq_last, tend, lane, h0, pu, pd, po, Bf, Cf, accB, accC, bl2, A2, Aln2, D2, G, dA2, dD2, db2);
-            --j;
-        }
-#pragma unroll 1
-        for (; j >= 0; --j) {
-            const float h0 = warp == 0 ? ck[j * 32] : fmaf(ex2f(Araw * ckm[j * 32]), hA, ck[j * 32]);
-            bwd_block<T, TO, kSoftplus, true>(tb + j * kBlk, 4, tend, lane, h0, pu, pd, po, Bf, Cf, accB, accC, bl2, A2, Aln2, D2, G, dA2, dD2, db2);
-        }
-        if (warp == 1) {
-            xch[64] = dA2.x + dA2.y; xch[96] = dD2.x + dD2.y; xch[128] = db2.x + db2.y;
-        }
-        fence_proxy_async();                             // du / ddelta tiles: generic-proxy writes -> bulk store
-        __syncthreads();
-        if (warp == 0) {
-            a.part_dA[(size_t)b * a.dim + d] = (dA2.x + dA2.y + xch[64]) * kLn2;
-            a.part_dD[(size_t)b * a.dim + d] = dD2.x + dD2.y + xch[96];
-            a.part_dbias[(size_t)b * a.dim + d] = db2.x + db2.y + xch[128];
-            if (lane == 0) {
-                bulk_s2g((char *)a.du + goff * es, tu, (uint32_t)(32 * L * es));
-                bulk_s2g((char *)a.ddelta + goff * es, td, (uint32_t)(32 * L * es));
-                bulk_commit();
-                bulk_wait_read<0>();                     // the tiles are refilled next: they must have been read out
+        float Gc = 0.f;                                  // warp 0: G at the first token of the chunk processed last
+
+        for (int c = nch - 1; c >= 0; --c) {
+            const int l0 = c * kRowsChunk, len = min(kRowsChunk, L - l0);
+            const int T0 = (len * 13 / 25) / 4 * 4;
+            const int tb = warp == 0 ? 0 : T0, tn = warp == 0 ? T0 : len - T0, tend = tb + tn;
+            const int nb = (tn + kBlk - 1) / kBlk;
+            const int nq_last = (tn - (nb - 1) * kBlk) / 4;              // quads of the half's last block
+            const size_t goff = ((size_t)b * a.dim + row0) * L + l0;     // first row of the tile
+            if (nch == 1) {
+                if (threadIdx.x == 0) {
+                    bulk_g2s(tu, (const char *)a.u + goff * es, (uint32_t)(32 * L * es), full);
+                    bulk_g2s(td, (const char *)a.delta + goff * es, (uint32_t)(32 * L * es), full);
+                    bulk_g2s(to, (const char *)a.dout + goff * eo, (uint32_t)(32 * L * eo), full);
+                    mbar_arrive_expect_tx(full, (uint32_t)(32 * L * (2 * es + eo)));
+                }
+            } else if (warp == 0) {                      // one piece per row and tensor, issued by the row's lane
+                const size_t gro = goff + (size_t)lane * L;
+                bulk_g2s(pu, (const char *)a.u + gro * es, (uint32_t)(len * es), full);
+                bulk_g2s(pd, (const char *)a.delta + gro * es, (uint32_t)(len * es), full);
+                bulk_g2s(const_cast<char *>(po), (const char *)a.dout + gro * eo, (uint32_t)(len * eo), full);
+                __syncwarp();
+                if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)(32 * len * (2 * es + eo)));
             }
+            {
+                const typename Cvt<T>::raw *gB = reinterpret_cast<const typename Cvt<T>::raw *>(a.B) + (size_t)b * a.B_bs + (size_t)g * a.B_gs + l0;
+                const typename Cvt<T>::raw *gC = reinterpret_cast<const typename Cvt<T>::raw *>(a.C) + (size_t)b * a.C_bs + (size_t)g * a.C_gs + l0;
+                for (int i = threadIdx.x; i < a.Lp; i += 64) {
+                    Bf[i] = i < len ? Cvt<T>::to_f(__ldg(gB + i)) * kLn2 : 0.f;
+                    Cf[i] = i < len ? Cvt<T>::to_f(__ldg(gC + i)) : 0.f;
+                }
+            }
+            const float hc = (warp == 0 && c > 0) ? xrow[c - 1].y : 0.f;   // state entering the chunk (forward checkpoint)
+            __syncthreads();                             // B', C rows complete
+            mbar_wait(full, phase);
+            phase ^= 1;
+
+            // ---- phase 1: states at the block boundaries of this warp's half (warp 1: local, from 0); exchange
+            float hend, Gs, Pt;
+            if (warp == 0) bwd_phase1<T, TO, kSoftplus, false>(tb, nb, nq_last, pu, pd, po, Bf, Cf, ck, ckm, bl2, A2, hc, hend, Gs, Pt);
+            else bwd_phase1<T, TO, kSoftplus, true>(tb, nb, nq_last, pu, pd, po, Bf, Cf, ck, ckm, bl2, A2, 0.f, hend, Gs, Pt);
+            float *gslot = xch + 160 + (c & 1) * 32;     // G entering this chunk from the next one (written by warp 0)
+            if (warp == 0) xch[0] = hend;
+            else {
+                const float Gin = c == nch - 1 ? 0.f : *gslot;
+                xch[32] = fmaf(Pt, Gin, Gs);             // suffix value handed to the last token of the first half
+                Gs = Gin;
+            }
+            __syncthreads();
+            const float hA = warp == 0 ? 0.f : xch[0];   // state entering the second half
+            float G = warp == 0 ? xch[32] : Gs;          // a_{t+1} g_{t+1}: what the suffix recurrence hands to token t
+
+            // ---- phase 2: this warp's blocks from last to first.  Only the last block of a half may be ragged: uniform
+            // guards, cold code; all the others are straight-line 16-token code the compiler can schedule across tokens
+            float *accB = a.acc_dB + (size_t)item * L + l0, *accC = a.acc_dC + (size_t)item * L + l0;
+            int j = nb - 1;
+            if (nb > 0 && nq_last < 4) {
+                const float h0 = warp == 0 ? ck[j * 32] : fmaf(ex2f(Araw * ckm[j * 32]), hA, ck[j * 32]);
+                bwd_block<T, TO, kSoftplus, false>(tb + j * kBlk, nq_last, tend, lane, h0, pu, pd, po, Bf, Cf, accB, accC, bl2, A2, Aln2, D2, G, dA2, dD2, db2);
+                --j;
+            }
+#pragma unroll 1
+            for (; j >= 0; --j) {
+                const float h0 = warp == 0 ? ck[j * 32] : fmaf(ex2f(Araw * ckm[j * 32]), hA, ck[j * 32]);
+                bwd_block<T, TO, kSoftplus, true>(tb + j * kBlk, 4, tend, lane, h0, pu, pd, po, Bf, Cf, accB, accC, bl2, A2, Aln2, D2, G, dA2, dD2, db2);
+            }
+            if (warp == 0) {
+                if (c > 0) xch[160 + ((c - 1) & 1) * 32] = G;            // for warp 1, one chunk earlier in the row
+            } else if (c == 0) {
+                xch[64] = dA2.x + dA2.y; xch[96] = dD2.x + dD2.y; xch[128] = db2.x + db2.y;
+            }
+            fence_proxy_async();                         // du / ddelta tiles: generic-proxy writes -> bulk store
+            __syncthreads();
+            if (warp == 0) {
+                if (c == 0) {
+                    a.part_dA[(size_t)b * a.dim + d] = (dA2.x + dA2.y + xch[64]) * kLn2;
+                    a.part_dD[(size_t)b * a.dim + d] = dD2.x + dD2.y + xch[96];
+                    a.part_dbias[(size_t)b * a.dim + d] = db2.x + db2.y + xch[128];
+                }
+                if (nch == 1) {
+                    if (lane == 0) {
+                        bulk_s2g((char *)a.du + goff * es, tu, (uint32_t)(32 * L * es));
+                        bulk_s2g((char *)a.ddelta + goff * es, td, (uint32_t)(32 * L * es));
+                        bulk_commit();
+                        bulk_wait_read<0>();             // the tiles are refilled next: they must have been read out
+                    }
+                } else {
+                    const size_t gro = goff + (size_t)lane * L;
+                    bulk_s2g((char *)a.du + gro * es, pu, (uint32_t)(len * es));
+                    bulk_s2g((char *)a.ddelta + gro * es, pd, (uint32_t)(len * es));
+                    bulk_commit();
+                    bulk_wait_read<0>();
+                    __syncwarp();
+                }
+            }
+            // no barrier here: warp 1 only touches B' / C rows (free since the barrier above) until the next one; the
+            // tiles are refilled by warp 0 after its wait, the xch slots are rewritten after the next barriers
         }
-        // no barrier here: warp 1 only touches B' / C rows (free since the barrier above) until the next one; the tiles
-        // are refilled by thread 0 after its wait, xch is rewritten after the next item's barriers
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }

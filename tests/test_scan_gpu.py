@@ -91,7 +91,8 @@ def test_scan_parity_small(shape, dtype, out_float):
 # Shapes the row-serial kernels take (d_state 1, delta per row, rows_per_group % 32 == 0, L % 4 == 0; the backward one
 # for L <= 256): block-boundary, ragged-last-block and single-quad cases of the 16-token recompute blocks.
 ROWS = [(2, 64, 196, 1, 2, 64), (1, 32, 4, 1, 1, 32), (2, 96, 16, 1, 3, 96), (1, 64, 20, 1, 1, 64), (2, 64, 256, 1, 2, 64),
-        (1, 32, 252, 1, 1, 32), (2, 128, 64, 1, 4, 128), (3, 32, 36, 1, 1, 32), (1, 64, 512, 1, 2, 64), (1, 32, 1000, 1, 1, 32)]
+        (1, 32, 252, 1, 1, 32), (2, 128, 64, 1, 4, 128), (3, 32, 36, 1, 1, 32), (1, 64, 512, 1, 2, 64), (1, 32, 1000, 1, 1, 32),
+        (2, 32, 260, 1, 1, 32), (1, 64, 776, 1, 2, 64), (2, 32, 264, 1, 1, 32), (1, 32, 2048, 1, 1, 32)]
 
 
 @pytest.mark.parametrize("shape", ROWS, ids=[f"b{s[0]}d{s[1]}L{s[2]}G{s[4]}" for s in ROWS])
