@@ -377,11 +377,11 @@ def main():
     bwd_gbs = per_gpu_tokens * bwd_b / (bwd_ms * 1e-3) / 1e9
     fwd_gbs = per_gpu_tokens * fwd_b / (fwd_ms * 1e-3) / 1e9
     step_gbs = (value / world) * (fwd_b + bwd_b) / 1e9
-    roofline = {"bound": "hbm", "kernel": "backward C-ABI call = ss_bwd_fast_kernel<bf16> + ss_finalize_kernel (timed together)",
+    roofline = {"bound": "hbm", "kernel": "backward C-ABI call = %s + ss_finalize_kernel (timed together)" % ("ss_bwd_rows_kernel<bf16>" if w["N"] == 1 else "ss_bwd_kernel<bf16>"),
                 "achieved": bwd_gbs, "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak,
                 "traffic": (ncu_traffic("bwd")[0] if args.workload == DEFAULT else None), "traffic_source": ncu_traffic("bwd")[1],
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": per_gpu_tokens * bwd_b,
-                "fwd_kernel": {"kernel": "forward C-ABI call = ss_fwd_rows_kernel<bf16>", "achieved": fwd_gbs, "frac": fwd_gbs / peak,
+                "fwd_kernel": {"kernel": "forward C-ABI call = %s" % ("ss_fwd_rows_kernel<bf16>" if w["N"] == 1 else "ss_fwd_kernel<bf16>"), "achieved": fwd_gbs, "frac": fwd_gbs / peak,
                                "algorithmic_bytes_per_launch": per_gpu_tokens * fwd_b},
                 "step": {"achieved": step_gbs, "frac": step_gbs / peak, "roofline_tokens_per_s": peak * 1e9 / (fwd_b + bwd_b)}}
     line = {"metric": METRIC, "value": value, "unit": "patch-tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
