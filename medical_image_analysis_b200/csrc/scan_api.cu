@@ -10,9 +10,11 @@
 #include "../../include/mia_selective_scan.h"
 #include "scan_common.cuh"
 #include "scan_bwd_rows.cuh"
+#include "scan_fwd_rowsn.cuh"
 
 namespace mia {
 template <typename T> cudaError_t launch_fwd_rows(const RowsArgs &, int, bool, cudaStream_t);
+template <typename T> cudaError_t launch_fwd_rowsn(const RowsNArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_rows(const RowsBwdArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_fwd_any(const ScanArgs &, int, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_any(const ScanArgs &, int, cudaStream_t);
@@ -269,6 +271,38 @@ bool plan_rows_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsArgs &
     return true;
 }
 
+// Row-serial forward for d_state > 1 (scan_fwd_rowsn.cuh): eligibility + argument block.
+bool plan_rowsn_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsNArgs &r, int &grid) {
+    const int es = esize(p.itype), L = p.seqlen, N = p.dstate;
+    const int rpg = p.dim / p.n_groups;
+    if ((N != 16 && N != 8) || p.z || p.delta_dim != p.dim || (rpg % 32) || (L % 4)) return false;
+    if (getenv("MIA_NO_ROWS_FWD")) return false;                // debugging knob: force the warp-scan kernels
+    if (mia_ss_num_chunks(L) != 1) return false;                // whole rows, one checkpoint
+    auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
+    if (!dense(p.u_batch_stride, p.u_d_stride) || !dense(p.delta_batch_stride, p.delta_d_stride) ||
+        !dense(p.out_batch_stride, p.out_d_stride)) return false;
+    if (((uintptr_t)p.u | (uintptr_t)p.delta | (uintptr_t)p.out) & 15) return false;
+    if ((32 * L * es) % 16) return false;
+    memset(&r, 0, sizeof(r));
+    r.batch = p.batch; r.dim = p.dim; r.L = L; r.G = p.n_groups; r.rows_per_group = rpg; r.N = N; r.softplus = p.delta_softplus;
+    const int W = mia::kRowsNWarps;
+    r.units_per_group = (rpg / 32 + W - 1) / W;
+    r.n_units = p.batch * p.n_groups * r.units_per_group;
+    r.tile_bytes = round_up(32 * L * es, 128);
+    r.off_bc = W * 2 * r.tile_bytes;
+    r.off_bar = r.off_bc + round_up(2 * L * N * es, 128);
+    r.smem_bytes = r.off_bar + 128;
+    const int per_sm = (int)((233472 - 0) / (r.smem_bytes + 1024));
+    if (per_sm < 1 || r.smem_bytes > di.smem_optin) return false;
+    r.u = p.u; r.delta = p.delta; r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.out = p.out; r.x = p.x;
+    r.A_ds = p.A_d_stride; r.A_ns = p.A_dstate_stride;
+    r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.B_ns = p.B_dstate_stride;
+    r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride; r.C_ns = p.C_dstate_stride;
+    grid = di.sms * (per_sm > 4 ? 4 : per_sm);
+    if (grid > r.n_units) grid = r.n_units;
+    return true;
+}
+
 // Row-serial backward (scan_bwd_rows.cuh): eligibility + argument block.  Returns false when the warp-scan kernels must run.
 bool plan_rows_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsBwdArgs &r, int &grid) {
     const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
@@ -445,6 +479,20 @@ int mia_selective_scan_fwd(const mia_ss_params *pp, void *cuda_stream) {
                 return (int)mia::launch_fwd_rows<T>(r, rgrid, of32, stream);
             });
             if (rc != 0) return fail(MIA_ECUDA, "selective_scan_fwd (row-serial) launch: %s", cudaGetErrorString((cudaError_t)rc));
+            g_launches.fetch_add(1);
+            return MIA_OK;
+        }
+    }
+    {
+        mia::RowsNArgs r;
+        int rgrid = 0;
+        if (plan_rowsn_fwd(p, di, r, rgrid)) {
+            const bool of32 = p.otype == MIA_F32 && p.itype != MIA_F32;
+            const int rc = dispatch(p.itype, [&](auto *tag) {
+                using T = typename std::remove_pointer<decltype(tag)>::type;
+                return (int)mia::launch_fwd_rowsn<T>(r, rgrid, of32, stream);
+            });
+            if (rc != 0) return fail(MIA_ECUDA, "selective_scan_fwd (row-serial, d_state %d) launch: %s", p.dstate, cudaGetErrorString((cudaError_t)rc));
             g_launches.fetch_add(1);
             return MIA_OK;
         }

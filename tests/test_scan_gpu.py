@@ -103,6 +103,19 @@ def test_scan_parity_row_serial(shape, dtype, out_float):
     _run_case(batch, dim, L, N, G, ddim, True, False, True, True, dtype, out_float, seed=5)
 
 
+# d_state 16 / 8 shapes the row-serial forward for d_state > 1 takes (whole rows in one tile; the backward is the warp-scan one)
+ROWSN = [(2, 64, 196, 16, 2, 64), (1, 32, 4, 16, 1, 32), (2, 96, 100, 8, 3, 96), (1, 64, 208, 16, 1, 64), (3, 32, 52, 16, 1, 32)]
+
+
+@pytest.mark.parametrize("shape", ROWSN, ids=[f"b{s[0]}d{s[1]}L{s[2]}N{s[3]}G{s[4]}" for s in ROWSN])
+@pytest.mark.parametrize("dtype,out_float", [(torch.float32, False), (torch.bfloat16, False), (torch.bfloat16, True),
+                                             (torch.float16, False)], ids=["f32", "bf16", "bf16o32", "f16"])
+def test_scan_parity_row_serial_dstate(shape, dtype, out_float):
+    batch, dim, L, N, G, ddim = shape
+    _run_case(batch, dim, L, N, G, ddim, True, False, True, True, dtype, out_float, seed=8)
+    _run_case(batch, dim, L, N, G, ddim, False, False, False, False, dtype, out_float, seed=9)
+
+
 @pytest.mark.parametrize("has_D,has_bias,softplus", list(itertools.product([False, True], repeat=3)))
 def test_scan_parity_row_serial_flags(has_D, has_bias, softplus):
     _run_case(2, 64, 196, 1, 2, 64, has_D, False, has_bias, softplus, torch.bfloat16, False, seed=6)
