@@ -10,6 +10,7 @@
 #include <type_traits>
 
 #include "scan_bwd.cuh"
+#include "scan_bwd_fastn.cuh"
 
 namespace mia {
 
@@ -230,12 +231,17 @@ __global__ void __launch_bounds__(kThreads, 1) ss_bwd_fast_kernel(const __grid_c
 
 template <typename T>
 cudaError_t launch_bwd_any(const ScanArgs &a, int grid, cudaStream_t stream) {
-    const bool fast = a.N == 1 && a.LPR == 32 && !a.has_z && a.delta_ratio == 1;
+    const bool fast = a.LPR == 32 && !a.has_z && a.delta_ratio == 1;
     if (!fast) return launch_bwd<T>(a, grid, stream);
     void (*kernel)(const ScanArgs);
     const bool of32 = a.out_f32 || sizeof(T) == 4;
-    if (a.softplus) kernel = of32 ? &ss_bwd_fast_kernel<T, true, true> : &ss_bwd_fast_kernel<T, true, false>;
-    else kernel = of32 ? &ss_bwd_fast_kernel<T, false, true> : &ss_bwd_fast_kernel<T, false, false>;
+    if (a.N == 1) {
+        if (a.softplus) kernel = of32 ? &ss_bwd_fast_kernel<T, true, true> : &ss_bwd_fast_kernel<T, true, false>;
+        else kernel = of32 ? &ss_bwd_fast_kernel<T, false, true> : &ss_bwd_fast_kernel<T, false, false>;
+    } else {
+        if (a.softplus) kernel = of32 ? &ss_bwd_fastn_kernel<T, true, true> : &ss_bwd_fastn_kernel<T, true, false>;
+        else kernel = of32 ? &ss_bwd_fastn_kernel<T, false, true> : &ss_bwd_fastn_kernel<T, false, false>;
+    }
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
     if (e != cudaSuccess) return e;
     kernel<<<grid, kThreads, a.smem_bytes, stream>>>(a);
