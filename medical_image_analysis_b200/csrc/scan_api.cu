@@ -11,10 +11,12 @@
 #include "scan_common.cuh"
 #include "scan_bwd_rows.cuh"
 #include "scan_fwd_rowsn.cuh"
+#include "scan_fwd_stream.cuh"
 
 namespace mia {
 template <typename T> cudaError_t launch_fwd_rows(const RowsArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_fwd_rowsn(const RowsNArgs &, int, bool, cudaStream_t);
+template <typename T> cudaError_t launch_fwd_stream(const StreamArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_rows(const RowsBwdArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_fwd_any(const ScanArgs &, int, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_any(const ScanArgs &, int, cudaStream_t);
@@ -271,6 +273,38 @@ bool plan_rows_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsArgs &
     return true;
 }
 
+// Streaming row-serial forward (scan_fwd_stream.cuh): eligibility + argument block.
+bool plan_stream_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::StreamArgs &r, int &grid) {
+    const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
+    const int rpg = p.dim / p.n_groups;
+    if (p.dstate != 1 || p.z || p.delta_dim != p.dim || (rpg % 32) || (L % 4)) return false;
+    if (getenv("MIA_NO_ROWS_FWD") || getenv("MIA_NO_STREAM_FWD")) return false;   // debugging knobs
+    auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
+    if (!dense(p.u_batch_stride, p.u_d_stride) || !dense(p.delta_batch_stride, p.delta_d_stride) ||
+        !dense(p.out_batch_stride, p.out_d_stride)) return false;
+    if (p.A_d_stride != 1 && p.dim > 1) return false;
+    const uintptr_t piece = 4 * es - 1, pieceo = 4 * eo - 1;    // every row start is a multiple of one 4-token piece
+    if ((((uintptr_t)p.u | (uintptr_t)p.delta) & piece) || ((uintptr_t)p.out & pieceo)) return false;
+    if (L > 256 && mia_ss_chunk_len(L) != 256) return false;
+    memset(&r, 0, sizeof(r));
+    r.batch = p.batch; r.dim = p.dim; r.L = L; r.G = p.n_groups; r.rows_per_group = rpg; r.softplus = p.delta_softplus;
+    r.n_items = p.batch * p.n_groups * (rpg / 32);
+    r.Lp = (L + 3) & ~3;
+    const int pitch = mia::kStreamTok * es + 4 * es;
+    r.off_bc32 = round_up(2 * 2 * 32 * pitch, 128);             // 2 stages x (u, delta)
+    r.smem_bytes = r.off_bc32 + round_up(2 * r.Lp * 4, 128);
+    if (r.smem_bytes > di.smem_optin) return false;
+    r.xchunks = mia_ss_num_chunks(L);
+    r.u = p.u; r.delta = p.delta; r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.out = p.out; r.x = p.x;
+    r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride;
+    int per_sm = (227 * 1024) / (r.smem_bytes + 1024);
+    if (per_sm > 16) per_sm = 16;                               // 128 registers per thread
+    if (per_sm < 4) return false;
+    grid = di.sms * per_sm;
+    if (grid > r.n_items) grid = r.n_items;
+    return true;
+}
+
 // Row-serial forward for d_state > 1 (scan_fwd_rowsn.cuh): eligibility + argument block.
 bool plan_rowsn_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsNArgs &r, int &grid) {
     const int es = esize(p.itype), L = p.seqlen, N = p.dstate;
@@ -479,6 +513,20 @@ int mia_selective_scan_fwd(const mia_ss_params *pp, void *cuda_stream) {
                 return (int)mia::launch_fwd_rows<T>(r, rgrid, of32, stream);
             });
             if (rc != 0) return fail(MIA_ECUDA, "selective_scan_fwd (row-serial) launch: %s", cudaGetErrorString((cudaError_t)rc));
+            g_launches.fetch_add(1);
+            return MIA_OK;
+        }
+    }
+    {
+        mia::StreamArgs r;
+        int rgrid = 0;
+        if (plan_stream_fwd(p, di, r, rgrid)) {
+            const bool of32 = p.otype == MIA_F32 && p.itype != MIA_F32;
+            const int rc = dispatch(p.itype, [&](auto *tag) {
+                using T = typename std::remove_pointer<decltype(tag)>::type;
+                return (int)mia::launch_fwd_stream<T>(r, rgrid, of32, stream);
+            });
+            if (rc != 0) return fail(MIA_ECUDA, "selective_scan_fwd (streaming) launch: %s", cudaGetErrorString((cudaError_t)rc));
             g_launches.fetch_add(1);
             return MIA_OK;
         }

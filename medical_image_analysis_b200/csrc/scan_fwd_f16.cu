@@ -2,8 +2,10 @@
 #include "scan_fwd_fast.cuh"
 #include "scan_fwd_rows.cuh"
 #include "scan_fwd_rowsn.cuh"
+#include "scan_fwd_stream.cuh"
 namespace mia {
 template cudaError_t launch_fwd_any<__half>(const ScanArgs &, int, cudaStream_t);
 template cudaError_t launch_fwd_rows<__half>(const RowsArgs &, int, bool, cudaStream_t);
 template cudaError_t launch_fwd_rowsn<__half>(const RowsNArgs &, int, bool, cudaStream_t);
+template cudaError_t launch_fwd_stream<__half>(const StreamArgs &, int, bool, cudaStream_t);
 }  // namespace mia
