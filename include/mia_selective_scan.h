@@ -122,6 +122,21 @@ int mia_selective_scan_bwd(const mia_ss_params *p, void *cuda_stream);
 int mia_cross_scan(const void *x, void *xs, int batch, int channels, int H, int W, int dtype, void *cuda_stream);
 int mia_cross_merge(const void *ys, void *y, int batch, int channels, int H, int W, int dtype, void *cuda_stream);
 
+/* Depth-wise causal conv1d (+ bias, + SiLU) of the Mamba mixers: y[b, d, t] = act(bias[d] + sum_k w[d, k] x[b, d, t - (K-1) + k]).
+ * Replaces causal_conv1d.causal_conv1d_fn (un-vendored; call sites arm/Finetuning/mamba_simple.py:676-681 of the three ARM sub-projects) == the in-repo
+ * fallback `self.act(self.conv1d(x)[..., :seqlen])` (:112-120, 673).  x, y, dy, dx: (batch, dim, seqlen), sequence stride 1,
+ * batch / channel strides in elements (multiples of 4; x is usually the first half of xz); weight (dim, width <= 4) and
+ * bias (dim, may be NULL) fp32 contiguous; seqlen % 4 == 0.  bwd writes dx, dweight (dim, width) and dbias (dim, if not
+ * NULL) completely (deterministic, no atomics).  mia_conv_last_error() holds the message of the last failure. */
+int mia_causal_conv1d_fwd(const void *x, const float *weight, const float *bias, void *y, int batch, int dim, int seqlen, int width,
+                          int silu, int dtype, long long x_batch_stride, long long x_d_stride, long long y_batch_stride,
+                          long long y_d_stride, void *cuda_stream);
+int mia_causal_conv1d_bwd(const void *x, const float *weight, const float *bias, const void *dy, void *dx, float *dweight, float *dbias,
+                          int batch, int dim, int seqlen, int width, int silu, int dtype, long long x_batch_stride, long long x_d_stride,
+                          long long dy_batch_stride, long long dy_d_stride, long long dx_batch_stride, long long dx_d_stride,
+                          void *cuda_stream);
+const char *mia_conv_last_error(void);
+
 /* Number of selective-scan kernel launches issued by this library in this process since load (bench.py gpu_launches). */
 uint64_t mia_launch_count(void);
 

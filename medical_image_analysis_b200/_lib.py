@@ -65,6 +65,12 @@ def lib() -> ctypes.CDLL:
         for fn in (L.mia_cross_scan, L.mia_cross_merge):
             fn.argtypes = [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]
             fn.restype = ctypes.c_int
+        ll, ci = ctypes.c_longlong, ctypes.c_int
+        L.mia_causal_conv1d_fwd.argtypes = [_vp, _vp, _vp, _vp, ci, ci, ci, ci, ci, ci, ll, ll, ll, ll, _vp]
+        L.mia_causal_conv1d_fwd.restype = ci
+        L.mia_causal_conv1d_bwd.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ci, ci, ci, ci, ci, ci, ll, ll, ll, ll, ll, ll, _vp]
+        L.mia_causal_conv1d_bwd.restype = ci
+        L.mia_conv_last_error.restype = ctypes.c_char_p
         if L.mia_abi_version() != 1:
             raise RuntimeError(f"libmia_scan.so ABI version {L.mia_abi_version()} != 1: rebuild it")
         _lib = L

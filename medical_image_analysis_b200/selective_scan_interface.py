@@ -161,13 +161,69 @@ def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_
 
 # ---------------------------------------------------------------------------------------------------------
 # Fused inner blocks of the Vim / ARM fork of mamba_ssm, composed (mamba_simple.py:665-709 is their definition).
+_CONV_DT = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def _conv_rows(t):
+    """(batch, dim, L) view with contiguous channel rows and a batch stride that is a multiple of 4 elements (the first
+    half of `xz` qualifies as it is); anything else is made contiguous."""
+    if t.stride(2) != 1 or t.stride(1) != t.shape[2] or t.stride(0) % 4 or t.data_ptr() % (4 * t.element_size()):
+        t = t.contiguous()
+    return t
+
+
+class CausalConv1dFn(torch.autograd.Function):
+    """Depth-wise causal conv1d (+ bias, + SiLU) through the C ABI (csrc/causal_conv1d.cu)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x, weight, bias, silu):
+        from . import _lib
+        if x.dim() != 3 or weight.dim() != 2 or weight.shape[0] != x.shape[1]:
+            raise RuntimeError("causal_conv1d_fn: x must be (batch, dim, seqlen) and weight (dim, width)")
+        if not x.is_cuda:
+            raise RuntimeError("causal_conv1d_fn: the B200 build has no CPU path (x must be a CUDA tensor)")
+        x = _conv_rows(x)
+        w32 = weight.detach().float().contiguous()
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        y = torch.empty(x.shape, device=x.device, dtype=x.dtype)
+        B, D, L = x.shape
+        rc = _lib.lib().mia_causal_conv1d_fwd(x.data_ptr(), w32.data_ptr(), 0 if b32 is None else b32.data_ptr(), y.data_ptr(), B, D, L,
+                                              weight.shape[1], int(silu), _CONV_DT[x.dtype], x.stride(0), x.stride(1), y.stride(0),
+                                              y.stride(1), torch.cuda.current_stream(x.device).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"causal_conv1d_fwd: {_lib.lib().mia_conv_last_error().decode()} (code {rc})")
+        ctx.save_for_backward(x, w32, b32 if b32 is not None else w32.new_empty(0))
+        ctx.silu, ctx.has_bias, ctx.wdtype, ctx.bdtype = bool(silu), bias is not None, weight.dtype, None if bias is None else bias.dtype
+        return y
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        from . import _lib
+        x, w32, b32 = ctx.saved_tensors
+        dy = _conv_rows(dy.to(x.dtype))
+        B, D, L = x.shape
+        dx = torch.empty(x.shape, device=x.device, dtype=x.dtype)
+        dw = torch.empty_like(w32)
+        db = torch.empty(D, device=x.device, dtype=torch.float32) if ctx.has_bias else None
+        rc = _lib.lib().mia_causal_conv1d_bwd(x.data_ptr(), w32.data_ptr(), b32.data_ptr() if ctx.has_bias else 0, dy.data_ptr(), dx.data_ptr(),
+                                              dw.data_ptr(), 0 if db is None else db.data_ptr(), B, D, L, w32.shape[1], int(ctx.silu),
+                                              _CONV_DT[x.dtype], x.stride(0), x.stride(1), dy.stride(0), dy.stride(1), dx.stride(0),
+                                              dx.stride(1), torch.cuda.current_stream(x.device).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"causal_conv1d_bwd: {_lib.lib().mia_conv_last_error().decode()} (code {rc})")
+        return dx, dw.to(ctx.wdtype), (db.to(ctx.bdtype) if db is not None else None), None
+
+
 def causal_conv1d_fn(x, weight, bias=None, activation=None):
     """causal_conv1d.causal_conv1d_fn: depthwise causal conv, x (b, d, l), weight (d, w); mamba_simple.py:673-681."""
     if activation not in (None, "silu", "swish"):
         raise NotImplementedError("activation must be None, silu or swish")
-    d, w = weight.shape
-    y = F.conv1d(x, weight.unsqueeze(1), bias, padding=w - 1, groups=d)[..., : x.shape[-1]]
-    return y if activation is None else F.silu(y)
+    L = x.shape[-1]
+    if L % 4:   # the kernels move 4-token pieces: pad on the right (a causal filter never looks there) and cut again
+        return CausalConv1dFn.apply(F.pad(x, (0, 4 - L % 4)), weight, bias, activation is not None)[..., :L]
+    return CausalConv1dFn.apply(x, weight, bias, activation is not None)
 
 
 def _inner_projections(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, B, C, B_proj_bias, C_proj_bias, d_state):
