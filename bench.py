@@ -266,12 +266,23 @@ def cpu_reference_run(w, steps, warmup, budget_s=150.0):
         return (u, delta, A, Bm, C, D, None, bias, True, dout)
 
     rows = R
-    probe_rows = min(R, 4 * G * 8)
+    probe_rows = min(R, 4 * G * 64)
     probe = mk(probe_rows)
-    selective_scan_ref_fwd_bwd(*probe)                            # warms torch's thread pool up
-    t0 = time.perf_counter()
-    selective_scan_ref_fwd_bwd(*probe)
-    t_probe = time.perf_counter() - t0
+    # "all the host threads it can use": torch's intra-op pool scales badly past the physical cores on this op (many small
+    # element-wise kernels per token), so time a probe at a few pool sizes and keep the fastest -- the baseline gets its
+    # best configuration, not the largest one
+    ncpu = os.cpu_count() or 1
+    best_t, best_n = None, None
+    for n in sorted({ncpu, max(1, ncpu // 2), max(1, ncpu // 4), min(ncpu, 32), min(ncpu, 16), min(ncpu, 8)}, reverse=True):
+        torch.set_num_threads(n)
+        selective_scan_ref_fwd_bwd(*probe)                        # warms torch's thread pool up
+        t0 = time.perf_counter()
+        selective_scan_ref_fwd_bwd(*probe)
+        t = time.perf_counter() - t0
+        if best_t is None or t < best_t:
+            best_t, best_n = t, n
+    torch.set_num_threads(best_n)
+    t_probe = best_t
     est = t_probe * R / probe_rows
     while rows > G * 8 and est * (steps + warmup) * rows / R > budget_s:
         rows //= 2

@@ -114,13 +114,11 @@ def test_dropin_registers_reference_module_names():
     assert out.strip().endswith("ok")
 
 
-def test_causal_conv1d_matches_reference_fallback():
-    """mamba_simple.py:673: act(conv1d(x)[..., :seqlen]) is the reference's own definition of causal_conv1d_fn."""
+def test_causal_conv1d_has_no_cpu_path():
+    """causal_conv1d_fn is a CUDA kernel behind the C ABI (parity vs mamba_simple.py:673 in tests/test_causal_conv1d_gpu.py);
+    like the scan it must fail loudly, not fall back, when it cannot run on the GPU."""
+    import pytest
     from medical_image_analysis_b200.selective_scan_interface import causal_conv1d_fn
-    torch.manual_seed(0)
-    d, w, L = 6, 4, 19
-    conv = torch.nn.Conv1d(d, d, w, groups=d, padding=w - 1)
-    x = torch.randn(2, d, L)
-    ref = torch.nn.functional.silu(conv(x)[..., :L])
-    got = causal_conv1d_fn(x, conv.weight.squeeze(1), conv.bias, "silu")
-    assert torch.allclose(got, ref, atol=1e-6)
+    conv = torch.nn.Conv1d(6, 6, 4, groups=6, padding=3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        causal_conv1d_fn(torch.randn(2, 6, 20), conv.weight.squeeze(1), conv.bias, "silu")
