@@ -200,7 +200,10 @@ bool layout_smem(mia::ScanArgs &a, int es, int eso, bool bwd, int smem_max) {
     const int bars = round_up((2 * mia::kMaxStages + 2 * mia::kGroupStages) * 8, 128);
     const int carry = round_up(bwd ? (2 * a.RS * a.N + 2 * a.RS) * 4 : a.RS * a.N * 8, 128);
     const int red = bwd ? a.n_consumer_warps * 256 * 4 : 0;
-    const int fixed = mia::kGroupStages * a.gstage_bytes + bars + carry + red;
+    // d_state > 1 fast backward (scan_bwd_fastn.cuh): the B / C chunk of all states once more as aligned fp32
+    const bool fastn = bwd && a.N > 1 && a.LPR == 32 && a.delta_ratio == 1;
+    const int bcf = fastn ? 2 * a.N * 256 * 4 : 0;
+    const int fixed = mia::kGroupStages * a.gstage_bytes + bars + carry + red + bcf;
     int stages = (smem_max - fixed) / a.stage_bytes;
     if (stages > mia::kMaxStages) stages = mia::kMaxStages;
     if (stages < 2) return false;
@@ -209,7 +212,8 @@ bool layout_smem(mia::ScanArgs &a, int es, int eso, bool bwd, int smem_max) {
     a.off_bars = a.off_groups + mia::kGroupStages * a.gstage_bytes;
     a.off_carry = a.off_bars + bars;
     a.off_red = a.off_carry + carry;
-    a.smem_bytes = a.off_red + red;
+    a.off_bcf = bcf ? a.off_red + red : 0;
+    a.smem_bytes = a.off_red + red + bcf;
     return true;
 }
 
@@ -309,26 +313,31 @@ bool plan_stream_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::StreamAr
 bool plan_rowsn_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsNArgs &r, int &grid) {
     const int es = esize(p.itype), L = p.seqlen, N = p.dstate;
     const int rpg = p.dim / p.n_groups;
-    if ((N != 16 && N != 8) || p.z || p.delta_dim != p.dim || (rpg % 32) || (L % 4)) return false;
+    if ((N != 16 && N != 8) || p.delta_dim != p.dim || (rpg % 32) || (L % 4)) return false;
     if (getenv("MIA_NO_ROWS_FWD")) return false;                // debugging knob: force the warp-scan kernels
     if (mia_ss_num_chunks(L) != 1) return false;                // whole rows, one checkpoint
     auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
     if (!dense(p.u_batch_stride, p.u_d_stride) || !dense(p.delta_batch_stride, p.delta_d_stride) ||
         !dense(p.out_batch_stride, p.out_d_stride)) return false;
     if (((uintptr_t)p.u | (uintptr_t)p.delta | (uintptr_t)p.out) & 15) return false;
+    if (p.z && (!dense(p.z_batch_stride, p.z_d_stride) || !dense(p.out_z_batch_stride, p.out_z_d_stride) ||
+                (((uintptr_t)p.z | (uintptr_t)p.out_z) & 15))) return false;
     if ((32 * L * es) % 16) return false;
     memset(&r, 0, sizeof(r));
     r.batch = p.batch; r.dim = p.dim; r.L = L; r.G = p.n_groups; r.rows_per_group = rpg; r.N = N; r.softplus = p.delta_softplus;
-    const int W = mia::kRowsNWarps;
+    r.warps = p.z ? 2 : mia::kRowsNWarps;
+    r.tiles_per_warp = p.z ? 3 : 2;
+    const int W = r.warps;
     r.units_per_group = (rpg / 32 + W - 1) / W;
     r.n_units = p.batch * p.n_groups * r.units_per_group;
     r.tile_bytes = round_up(32 * L * es, 128);
-    r.off_bc = W * 2 * r.tile_bytes;
+    r.off_bc = W * r.tiles_per_warp * r.tile_bytes;
     r.off_bar = r.off_bc + round_up(2 * L * N * es, 128);
     r.smem_bytes = r.off_bar + 128;
-    const int per_sm = (int)((233472 - 0) / (r.smem_bytes + 1024));
+    const int per_sm = (int)(233472 / (r.smem_bytes + 1024));
     if (per_sm < 1 || r.smem_bytes > di.smem_optin) return false;
     r.u = p.u; r.delta = p.delta; r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.out = p.out; r.x = p.x;
+    r.z = p.z; r.out_z = p.out_z;
     r.A_ds = p.A_d_stride; r.A_ns = p.A_dstate_stride;
     r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.B_ns = p.B_dstate_stride;
     r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride; r.C_ns = p.C_dstate_stride;
@@ -598,6 +607,7 @@ int mia_selective_scan_bwd(const mia_ss_params *pp, void *cuda_stream) {
     a.acc_dB = (float *)(ws + w.acc_dB); a.acc_dC = (float *)(ws + w.acc_dC);
     a.ddelta_full = (float *)(ws + w.ddelta_full);
     a.bc_atomic = w.bc_atomic;
+    if (w.bc_atomic && getenv("MIA_DEBUG_SKIP_RED")) a.bc_atomic = 2;   // timing experiment only: dB / dC are wrong
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     if (w.bc_atomic) {
         MIA_CUDA(cudaMemsetAsync(a.acc_dB, 0, w.acc_bytes, stream));

@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) ss_bwd_fast_kernel(const __grid_c
 
 template <typename T>
 cudaError_t launch_bwd_any(const ScanArgs &a, int grid, cudaStream_t stream) {
-    const bool fast = a.LPR == 32 && !a.has_z && a.delta_ratio == 1;
+    const bool fast = a.LPR == 32 && a.delta_ratio == 1 && (a.N > 1 || !a.has_z);
     if (!fast) return launch_bwd<T>(a, grid, stream);
     void (*kernel)(const ScanArgs);
     const bool of32 = a.out_f32 || sizeof(T) == 4;

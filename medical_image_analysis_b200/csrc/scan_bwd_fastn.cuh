@@ -1,4 +1,5 @@
-// Backward selective scan, fast path for d_state > 1: rows spanning the whole warp (L > 128), delta per row, no z gate.
+// Backward selective scan, fast path for d_state > 1: rows spanning the whole warp (L > 128), delta per row, with or
+// without the z gate of the mamba_ssm signature.
 // Same pipeline (producer warp, group / row stages), reductions and results as the generic kernel (scan_bwd.cuh); the
 // consumer is rewritten for instruction count -- the generic kernel executes 7750 warp-instructions per row at N = 16
 // (ncu), twice what the arithmetic needs:
@@ -74,6 +75,20 @@ __global__ void __launch_bounds__(kThreads, 1) ss_bwd_fastn_kernel(const __grid_
             const char *gC = (const char *)a.C + ((size_t)sc.b * a.C_bs + (size_t)sc.g * a.C_gs + l0) * es;
             const RowView vB = make_view(gs + a.goff_B, gB, a.B_ns, len, es, a.bc_pitch, a.flat_B);
             const RowView vC = make_view(gs + a.goff_C, gC, a.C_ns, len, es, a.bc_pitch, a.flat_C);
+            // B / C of this (segment, chunk) once more as aligned fp32, [tensor][state][half: tokens 0-3 / 4-7 of a lane][lane]
+            // float4s: the per-state loads of the row loop become four conflict-free LDS.128 without conversion or
+            // alignment dispatch.  One consumer barrier before (the previous chunk's readers are done) and one after.
+            float4 *bcf = reinterpret_cast<float4 *>(smem + a.off_bcf);
+            consumer_bar(NW * 32);
+            for (int idx = warp; idx < 2 * N; idx += NW) {
+                const int n = idx >> 1;
+                float2 v[4];
+                lds8v<T>(((idx & 1) ? vC : vB).row(n) + tok0 * es, v);
+                float4 *dst = bcf + (size_t)idx * 64;
+                dst[lane] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+                dst[32 + lane] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+            }
+            consumer_bar(NW * 32);
             const float *pA = reinterpret_cast<const float *>(gs + a.goff_A);
             const float *pD = reinterpret_cast<const float *>(gs + a.goff_D);
             const float *pbias = reinterpret_cast<const float *>(gs + a.goff_bias);
@@ -82,6 +97,8 @@ __global__ void __launch_bounds__(kThreads, 1) ss_bwd_fastn_kernel(const __grid_
             const uint32_t go_lo = (uint32_t)(uintptr_t)((const char *)a.dout + ((size_t)sc.b * a.dout_bs + (size_t)sc.row_lo * a.dout_ds + l0) * eso);
             char *du_seg = (char *)a.du + ((size_t)sc.b * a.du_bs + (size_t)sc.row_lo * a.du_ds + l0 + tok0) * es;
             char *dd_seg = (char *)a.ddelta + ((size_t)sc.b * a.dd_bs + (size_t)sc.row_lo * a.dd_ds + l0 + tok0) * es;
+            char *dz_seg = a.has_z ? (char *)a.dz + ((size_t)sc.b * a.dz_bs + (size_t)sc.row_lo * a.dz_ds + l0 + tok0) * es : nullptr;
+            const size_t dz_step = (size_t)a.dz_ds * es;
             float *accB = a.acc_dB + (size_t)(sc.b * a.G + sc.g) * N * Lp + l0 + tok0;
             float *accC = a.acc_dC + (size_t)(sc.b * a.G + sc.g) * N * Lp + l0 + tok0;
             for (int t = 0; t < tiles; ++t, ++kr) {
@@ -93,12 +110,35 @@ __global__ void __launch_bounds__(kThreads, 1) ss_bwd_fastn_kernel(const __grid_
                 const uint32_t d_t = stb + a.off_delta + tok0 * es, dlo_t = gd_lo + r0 * dstepB;
                 const uint32_t o_t = stb + a.off_dout + tok0 * eso, olo_t = go_lo + r0 * ostepB;
                 const float *h0s = reinterpret_cast<const float *>(smem + (size_t)sr * a.stage_bytes + a.off_h0);
+                RowView vz{}, vo{};
+                if (a.has_z) {
+                    const char *st = smem + (size_t)sr * a.stage_bytes;
+                    const size_t d0 = (size_t)sc.row_lo + r0;
+                    vz = make_view(st + a.off_z, (const char *)a.z + ((size_t)sc.b * a.z_bs + d0 * a.z_ds + l0) * es, a.z_ds, len, es,
+                                   a.row_pitch, a.flat_z);
+                    vo = make_view(st + a.off_osaved, (const char *)a.out_saved + ((size_t)sc.b * a.osaved_bs + d0 * a.osaved_ds + l0) * eso,
+                                   a.osaved_ds, len, eso, a.rowo_pitch, a.flat_osaved);
+                }
                 for (int r = warp; r < nr; r += NW) {
                     const int rs = r0 + r;
                     float2 m2[4], u2[4], dy2[4];
                     lds8v<T>(d_t + r * dpitch + ((dlo_t + r * dstep) & 15u), m2);
                     lds8v<T>(u_t + r * upitch + ((ulo_t + r * ustep) & 15u), u2);
                     lds8v<TO>(o_t + r * opitch + ((olo_t + r * ostep) & 15u), dy2);
+                    if (a.has_z) {
+                        // out_z = y silu(z):  dy = dout silu(z);  dz = dout y sigmoid(z) (1 + z (1 - sigmoid(z)))   (y = saved `out`)
+                        float2 z2[4], o2[4], dz2[4];
+                        lds8v<T>(vz.row(r) + tok0 * es, z2);
+                        lds8v<TO>(vo.row(r) + tok0 * eso, o2);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float2 sz = make_float2(rcpf(1.f + ex2f(-z2[k].x * kLog2e)), rcpf(1.f + ex2f(-z2[k].y * kLog2e)));
+                            const float2 dsz = mul2(dy2[k], sz);
+                            dz2[k] = mul2(mul2(dsz, o2[k]), make_float2(fmaf(z2[k].x, 1.f - sz.x, 1.f), fmaf(z2[k].y, 1.f - sz.y, 1.f)));
+                            dy2[k] = mul2(dsz, z2[k]);
+                        }
+                        if (nval > 0) st8v<T>(dz_seg + (size_t)rs * dz_step, dz2, nval);
+                    }
                     // tokens past the end of the sequence come FIRST in the suffix scan: their dy must be zero
                     if (nval < kTok) {
 #pragma unroll
@@ -110,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) ss_bwd_fastn_kernel(const __grid_
                     const float Dv = pD[rs];
                     const float2 bl = splat2(pbias[rs] * kLog2e);
                     float2 mul2v[4], dum2[4], ddl2[4];       // m u ln2 (= dl u); du in units of 1/ln2; d(dl)
-                    float dDv = 0.f;
+                    float dDv = 0.f, msum = 0.f;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         float2 m = fma2(m2[k], kL2E, bl);       // (delta + bias) * log2e
@@ -120,6 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) ss_bwd_fastn_kernel(const __grid_
                             m = make_float2(fmaxf(lg2f(s.x), m.x), fmaxf(lg2f(s.y), m.y));      // softplus * log2e
                         }
                         m2[k] = m;
+                        msum += m.x + m.y;
                         mul2v[k] = mul2(mul2(m, u2[k]), kLN2);
                         dum2[k] = make_float2(0.f, 0.f);
                         ddl2[k] = make_float2(0.f, 0.f);
@@ -130,22 +171,30 @@ __global__ void __launch_bounds__(kThreads, 1) ss_bwd_fastn_kernel(const __grid_
                     const float *h0r = h0s + r * N;
                     float *cGr = carryG + rs * N, *cAr = carryA + rs * N;
                     float *gdA = a.part_dA + (size_t)(sc.b * a.dim + sc.row_lo + rs) * N;
+                    float *pB = accB, *pC = accC;            // accumulator rows of state n (advance by Lp per state)
 #pragma unroll 1
                     for (int n = 0; n < N; ++n) {
                         const float Araw = pAr[n] * kLn2;       // the group stage holds A * log2e
                         float2 B2[4], C2[4], a2[4], ah2[4];
-                        lds8v<T>(vB.row(n) + tok0 * es, B2);
-                        lds8v<T>(vC.row(n) + tok0 * es, C2);
+                        {
+                            const float4 *src = bcf + (size_t)n * 128 + lane;
+                            const float4 b0 = src[0], b1 = src[32], c0 = src[64], c1 = src[96];
+                            B2[0] = make_float2(b0.x, b0.y); B2[1] = make_float2(b0.z, b0.w);
+                            B2[2] = make_float2(b1.x, b1.y); B2[3] = make_float2(b1.z, b1.w);
+                            C2[0] = make_float2(c0.x, c0.y); C2[1] = make_float2(c0.z, c0.w);
+                            C2[2] = make_float2(c1.x, c1.y); C2[3] = make_float2(c1.z, c1.w);
+                        }
                         // ---- forward recompute: lane aggregate, warp scan, per-token states
-                        float pa = 1.f, pb = 0.f;
+                        float pa = ex2f(msum * Araw), pb = 0.f;  // product of the lane's 8 a: one MUFU instead of 8 FMUL
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const float2 arg = mul2(m2[k], splat2(Araw));
                             a2[k] = make_float2(ex2f(arg.x), ex2f(arg.y));
                             ah2[k] = mul2(mul2v[k], B2[k]);     // b_t for now
-                            pb = fmaf(a2[k].x, pb, ah2[k].x); pa *= a2[k].x;
-                            pb = fmaf(a2[k].y, pb, ah2[k].y); pa *= a2[k].y;
+                            pb = fmaf(a2[k].x, pb, ah2[k].x);
+                            pb = fmaf(a2[k].y, pb, ah2[k].y);
                         }
+                        float ra = pa, rb = 0.f;                 // the suffix scan multiplies the same 8 factors
                         const float h0 = first_chunk ? 0.f : h0r[n];
                         float ea, eb;
                         seg_scan_fwd<32>(pa, pb, ea, eb, lane, 32);
@@ -158,17 +207,16 @@ __global__ void __launch_bounds__(kThreads, 1) ss_bwd_fastn_kernel(const __grid_
                             tt = a2[k].y * hm; hm = tt + ah2[k].y; ah2[k].y = tt; hh.y = hm;
                             dCv[k] = mul2(dy2[k], hh);
                         }
-                        if (nval > 0) {
-                            red_add_v4(accC + (size_t)n * Lp, dCv[0].x, dCv[0].y, dCv[1].x, dCv[1].y);
-                            if (nval > 4) red_add_v4(accC + (size_t)n * Lp + 4, dCv[2].x, dCv[2].y, dCv[3].x, dCv[3].y);
+                        if (nval > 0 && a.bc_atomic != 2) {
+                            red_add_v4(pC, dCv[0].x, dCv[0].y, dCv[1].x, dCv[1].y);
+                            if (nval > 4) red_add_v4(pC + 4, dCv[2].x, dCv[2].y, dCv[3].x, dCv[3].y);
                         }
                         // ---- suffix scan of G_t = a_t (dy_t C_t + G_{t+1})
-                        float ra = 1.f, rb = 0.f;
 #pragma unroll
                         for (int k = 3; k >= 0; --k) {
                             C2[k] = mul2(dy2[k], C2[k]);        // dy C
-                            rb = a2[k].y * (C2[k].y + rb); ra *= a2[k].y;
-                            rb = a2[k].x * (C2[k].x + rb); ra *= a2[k].x;
+                            rb = a2[k].y * (C2[k].y + rb);
+                            rb = a2[k].x * (C2[k].x + rb);
                         }
                         const float gin = last_chunk ? 0.f : cGr[n];
                         seg_scan_rev<32>(ra, rb, ea, eb, lane, 32);
@@ -187,10 +235,11 @@ __global__ void __launch_bounds__(kThreads, 1) ss_bwd_fastn_kernel(const __grid_
                             dAm2 = fma2(gah, m2[k], dAm2);                      // dA / ln2
                             B2[k] = mul2(g, mul2v[k]);                          // dB
                         }
-                        if (nval > 0) {
-                            red_add_v4(accB + (size_t)n * Lp, B2[0].x, B2[0].y, B2[1].x, B2[1].y);
-                            if (nval > 4) red_add_v4(accB + (size_t)n * Lp + 4, B2[2].x, B2[2].y, B2[3].x, B2[3].y);
+                        if (nval > 0 && a.bc_atomic != 2) {
+                            red_add_v4(pB, B2[0].x, B2[0].y, B2[1].x, B2[1].y);
+                            if (nval > 4) red_add_v4(pB + 4, B2[2].x, B2[2].y, B2[3].x, B2[3].y);
                         }
+                        pB += Lp; pC += Lp;
                         if (!first_chunk) {
                             __syncwarp();
                             if (lane == 0) cGr[n] = Gn;         // G at this chunk's first token, for chunk c-1

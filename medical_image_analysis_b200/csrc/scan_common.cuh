@@ -40,7 +40,8 @@ struct ScanArgs {
     int row_pitch, rowo_pitch, bc_pitch;
     int off_u, off_delta, off_z, off_dout, off_osaved, off_h0, stage_bytes;   // inside a row stage
     int goff_B, goff_C, goff_A, goff_D, goff_bias, gstage_bytes;              // inside a group stage
-    int off_groups, off_bars, off_carry, off_red, smem_bytes;                 // row stages start at 0
+    int off_groups, off_bars, off_carry, off_red, off_bcf, smem_bytes;        // row stages start at 0; off_bcf: fp32 B/C chunk
+                                                                              // of the d_state > 1 fast backward (0 = absent)
     // pointers
     const void *u, *delta, *A, *B, *C, *D, *delta_bias, *z;
     void *out, *out_z;

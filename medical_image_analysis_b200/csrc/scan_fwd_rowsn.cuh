@@ -11,7 +11,9 @@
 //     group are transposed once per group into token-major rows [t][kN] in shared memory (element type T: fp32 rows
 //     would cost a resident CTA), so that every token needs kN/8 broadcast LDS.128 per tensor and one ALU op per value;
 //   * log2 domain throughout: m = softplus(delta + bias) log2e, a_n = 2^(m A_n), b_n = (m u) (B_n ln2).
-// Preconditions (host-checked, otherwise the warp-scan kernels run): d_state == kN, delta per row, no z, whole rows in
+// With the z gate of the mamba_ssm signature the z tile is a third tile per warp (2 warps per CTA), out_z = y silu(z)
+// overwrites it and leaves with a second bulk store; `out` (y before the gate) is still written: the backward needs it.
+// Preconditions (host-checked, otherwise the warp-scan kernels run): d_state == kN, delta per row, whole rows in
 // the tile (32 L es <= tile budget), rows contiguous, rows_per_group % 32 == 0, L % 4 == 0, 16-byte aligned tiles.
 #pragma once
 #include <type_traits>
@@ -20,15 +22,16 @@
 
 namespace mia {
 
-constexpr int kRowsNWarps = 4;   // warps per CTA: each owns a 32-row batch, all share the B / C rows of the (batch, group)
+constexpr int kRowsNWarps = 4;   // max warps per CTA: each owns a 32-row batch, all share the B / C rows of the (batch, group)
 
 struct RowsNArgs {
     int batch, dim, L, G, rows_per_group, N;
     int softplus;
-    int n_units, units_per_group;         // unit = kRowsNWarps consecutive 32-row batches of one (batch, group)
+    int n_units, units_per_group;         // unit = `warps` consecutive 32-row batches of one (batch, group)
+    int warps, tiles_per_warp;            // 4 warps x (u, delta) tiles, or 2 warps x (u, delta, z) with the z gate
     int tile_bytes, off_bc, off_bar, smem_bytes;
-    const void *u, *delta, *A, *B, *C, *D, *delta_bias;
-    void *out;
+    const void *u, *delta, *A, *B, *C, *D, *delta_bias, *z;
+    void *out, *out_z;                    // out_z = out * silu(z) (mamba_ssm signature), both written when z is given
     float *x;                             // (batch, dim, 1, 2 N): (prod a_n, h_n) at the row end
     long long A_ds, A_ns, B_bs, B_gs, B_ns, C_bs, C_gs, C_ns;
 };
@@ -73,7 +76,7 @@ template <int kN> struct StateRow<float, kN> {
     }
 };
 
-template <typename T, bool kSoftplus, bool kOutF32, int kN>
+template <typename T, bool kSoftplus, bool kOutF32, int kN, bool kHasZ>
 __global__ void __launch_bounds__(32 * kRowsNWarps) ss_fwd_rowsn_kernel(const __grid_constant__ RowsNArgs a) {
     static_assert(kN % 8 == 0, "states are loaded eight at a time and processed as packed pairs");
     extern __shared__ __align__(128) char smem[];
@@ -82,7 +85,8 @@ __global__ void __launch_bounds__(32 * kRowsNWarps) ss_fwd_rowsn_kernel(const __
     using raw = typename Cvt<T>::raw;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int L = a.L;
-    char *tu = smem + (size_t)warp * 2 * a.tile_bytes, *td = tu + a.tile_bytes;
+    const int W = blockDim.x >> 5;
+    char *tu = smem + (size_t)warp * a.tiles_per_warp * a.tile_bytes, *td = tu + a.tile_bytes, *tz = td + a.tile_bytes;
     raw *Bs = reinterpret_cast<raw *>(smem + a.off_bc), *Cs = Bs + (size_t)L * kN;     // [t][kN], element type T
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + a.off_bar) + warp;
     if (lane == 0) { mbar_init(full, 1); fence_mbar_init(); }
@@ -95,6 +99,7 @@ __global__ void __launch_bounds__(32 * kRowsNWarps) ss_fwd_rowsn_kernel(const __
     const float2 kL2E = splat2(kLog2e), kOne = splat2(1.f);
     char *pu = tu + (size_t)lane * L * es;
     const char *pd = td + (size_t)lane * L * es;
+    char *pz = tz + (size_t)lane * L * es;
     uint32_t phase = 0;
 
     // contiguous unit ranges per CTA (the first `rem` CTAs take one more): consecutive units share (batch, group), so the
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(32 * kRowsNWarps) ss_fwd_rowsn_kernel(const __
     int bg_loaded = -1;
     for (int unit = unit_begin; unit < unit_end; ++unit) {
         const int bg = unit / a.units_per_group;
-        const int bt = (unit % a.units_per_group) * kRowsNWarps + warp;
+        const int bt = (unit % a.units_per_group) * W + warp;
         const bool valid = bt < batches_per_group;       // warp-uniform
         const int g = bg % a.G, b = bg / a.G;
         const int row0 = g * a.rows_per_group + (valid ? bt : 0) * 32;
@@ -114,7 +119,8 @@ __global__ void __launch_bounds__(32 * kRowsNWarps) ss_fwd_rowsn_kernel(const __
         if (valid && lane == 0) {
             bulk_g2s(tu, (const char *)a.u + goff * es, (uint32_t)(32 * L * es), full);
             bulk_g2s(td, (const char *)a.delta + goff * es, (uint32_t)(32 * L * es), full);
-            mbar_arrive_expect_tx(full, 2u * 32u * L * es);
+            if (kHasZ) bulk_g2s(tz, (const char *)a.z + goff * es, (uint32_t)(32 * L * es), full);
+            mbar_arrive_expect_tx(full, (kHasZ ? 3u : 2u) * 32u * L * es);
         }
         // B, C of the group: global [n][t] (sequence contiguous) -> shared [t][kN].  Flat index = t * kN + n: the shared
         // stores of a warp are consecutive elements, the global loads kN rows x 32 / kN tokens; 8 + 8 loads per thread
@@ -124,7 +130,8 @@ __global__ void __launch_bounds__(32 * kRowsNWarps) ss_fwd_rowsn_kernel(const __
             __syncthreads();                             // every warp is done with the previous group's rows
             const raw *gB = reinterpret_cast<const raw *>(a.B) + (size_t)b * a.B_bs + (size_t)g * a.B_gs;
             const raw *gC = reinterpret_cast<const raw *>(a.C) + (size_t)b * a.C_bs + (size_t)g * a.C_gs;
-            constexpr int kU = 8, kStep = 32 * kRowsNWarps;
+            constexpr int kU = 8;
+            const int kStep = blockDim.x;
             const int tot = L * kN;
             for (int base = 0; base < tot; base += kStep * kU) {
                 raw vb[kU], vc[kU];
@@ -156,6 +163,7 @@ __global__ void __launch_bounds__(32 * kRowsNWarps) ss_fwd_rowsn_kernel(const __
         mbar_wait(full, phase);
         phase ^= 1;
         char *orow = kOutF32 ? (char *)a.out + (goff + (size_t)lane * L) * 4 : nullptr;
+        char *ozrow = (kOutF32 && kHasZ) ? (char *)a.out_z + (goff + (size_t)lane * L) * 4 : nullptr;
 
 #pragma unroll 1
         for (int t = 0; t < L; t += 4) {
@@ -194,6 +202,17 @@ __global__ void __launch_bounds__(32 * kRowsNWarps) ss_fwd_rowsn_kernel(const __
             y[1] = make_float2(ys[2], ys[3]);
             if (kOutF32) *reinterpret_cast<float4 *>(orow + (size_t)t * 4) = make_float4(ys[0], ys[1], ys[2], ys[3]);
             else Quad<T>::st(pu + t * es, y);                // y replaces u in place
+            if (kHasZ) {                                     // out_z = y * silu(z), computed from the unrounded y
+                float2 zz[2], yz[2];
+                Quad<T>::ld(pz + t * es, zz);
+#pragma unroll
+                for (int qq = 0; qq < 2; ++qq) {
+                    const float2 sz = make_float2(rcpf(1.f + ex2f(-zz[qq].x * kLog2e)), rcpf(1.f + ex2f(-zz[qq].y * kLog2e)));
+                    yz[qq] = mul2(mul2(y[qq], zz[qq]), sz);
+                }
+                if (kOutF32) *reinterpret_cast<float4 *>(ozrow + (size_t)t * 4) = make_float4(yz[0].x, yz[0].y, yz[1].x, yz[1].y);
+                else Quad<T>::st(pz + t * es, yz);           // out_z replaces z in place
+            }
         }
         // checkpoint at the row end: (prod a_n, h_n) interleaved, prod a_n = 2^(A_n sum m)
         {
@@ -207,6 +226,7 @@ __global__ void __launch_bounds__(32 * kRowsNWarps) ss_fwd_rowsn_kernel(const __
             __syncwarp();
             if (lane == 0) {
                 bulk_s2g((char *)a.out + goff * es, tu, (uint32_t)(32 * L * es));
+                if (kHasZ) bulk_s2g((char *)a.out_z + goff * es, tz, (uint32_t)(32 * L * es));
                 bulk_commit();
                 bulk_wait_read<0>();                        // the tile is refilled next: it must have been read out
             }
@@ -216,21 +236,22 @@ __global__ void __launch_bounds__(32 * kRowsNWarps) ss_fwd_rowsn_kernel(const __
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA retires
 }
 
+template <typename T, int kN, bool kHasZ>
+void (*pick_fwd_rowsn(bool softplus, bool out_f32))(const RowsNArgs) {
+    if (softplus) return out_f32 ? &ss_fwd_rowsn_kernel<T, true, true, kN, kHasZ> : &ss_fwd_rowsn_kernel<T, true, false, kN, kHasZ>;
+    return out_f32 ? &ss_fwd_rowsn_kernel<T, false, true, kN, kHasZ> : &ss_fwd_rowsn_kernel<T, false, false, kN, kHasZ>;
+}
+
 template <typename T>
 cudaError_t launch_fwd_rowsn(const RowsNArgs &a, int grid, bool out_f32, cudaStream_t stream) {
     void (*kernel)(const RowsNArgs) = nullptr;
-    if (a.N == 16) {
-        if (a.softplus) kernel = out_f32 ? &ss_fwd_rowsn_kernel<T, true, true, 16> : &ss_fwd_rowsn_kernel<T, true, false, 16>;
-        else kernel = out_f32 ? &ss_fwd_rowsn_kernel<T, false, true, 16> : &ss_fwd_rowsn_kernel<T, false, false, 16>;
-    } else if (a.N == 8) {
-        if (a.softplus) kernel = out_f32 ? &ss_fwd_rowsn_kernel<T, true, true, 8> : &ss_fwd_rowsn_kernel<T, true, false, 8>;
-        else kernel = out_f32 ? &ss_fwd_rowsn_kernel<T, false, true, 8> : &ss_fwd_rowsn_kernel<T, false, false, 8>;
-    } else {
-        return cudaErrorInvalidValue;
-    }
+    const bool sp = a.softplus != 0, hz = a.z != nullptr;
+    if (a.N == 16) kernel = hz ? pick_fwd_rowsn<T, 16, true>(sp, out_f32) : pick_fwd_rowsn<T, 16, false>(sp, out_f32);
+    else if (a.N == 8) kernel = hz ? pick_fwd_rowsn<T, 8, true>(sp, out_f32) : pick_fwd_rowsn<T, 8, false>(sp, out_f32);
+    else return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
     if (e != cudaSuccess) return e;
-    kernel<<<grid, 32 * kRowsNWarps, a.smem_bytes, stream>>>(a);
+    kernel<<<grid, 32 * a.warps, a.smem_bytes, stream>>>(a);
     return cudaGetLastError();
 }
 

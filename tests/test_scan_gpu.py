@@ -128,6 +128,16 @@ def test_scan_parity_flags(has_D, has_z, has_bias, softplus, dtype):
     _run_case(2, 16, 100, 4, 2, 16, has_D, has_z, has_bias, softplus, dtype, False, seed=3)
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 196, 16, 1, 16), (1, 8, 300, 4, 2, 8), (2, 32, 197, 16, 1, 32), (2, 64, 196, 16, 2, 64), (1, 32, 100, 8, 1, 32)],
+                         ids=lambda s: f"b{s[0]}d{s[1]}L{s[2]}N{s[3]}G{s[4]}")
+@pytest.mark.parametrize("dtype,out_float", [(torch.float32, False), (torch.bfloat16, False), (torch.bfloat16, True)], ids=["f32", "bf16", "bf16o32"])
+def test_scan_parity_z_gate_fast_backward(shape, dtype, out_float):
+    """The mamba_ssm signature (z gate) on rows spanning a whole warp: the d_state > 1 fast backward with dz; the last
+    two shapes also take the row-serial forward with the z tile."""
+    batch, dim, L, N, G, ddim = shape
+    _run_case(batch, dim, L, N, G, ddim, True, True, True, True, dtype, out_float, seed=12)
+
+
 def test_scan_golden_reference_vectors():
     """CUDA path vs the vectors produced by the reference's own selective_scan_ref + autograd (tests/golden)."""
     from medical_image_analysis_b200 import scan_bwd, scan_fwd
