@@ -32,6 +32,9 @@ WORKLOADS = {
     "ss2d_m6400_n16": dict(B=4, R=3072, G=4, L=6400, N=16, out_f32=False),
     "ss2d_m196_n1_o32": dict(B=64, R=3072, G=4, L=196, N=1, out_f32=True),
     "ss2d_m196_n16_o32": dict(B=64, R=3072, G=4, L=196, N=16, out_f32=True),
+    # the scan of one direction of the ARM / Vim mixer (MambaXray-VL-Base: d_model 768, expand 2 -> 1536 rows, one B/C
+    # group, d_state 16, z gate; arm/Finetuning/mamba_simple.py:693-704)
+    "arm_m196_n16_z": dict(B=64, R=1536, G=1, L=196, N=16, out_f32=False, z=True),
 }
 DEFAULT = "ss2d_m196_n1"
 METRIC = "patch-tokens/sec SS2D fwd+bwd at L=196/6400 D=768; % HBM roofline"
@@ -43,6 +46,9 @@ def bytes_per_token(w, es=2):
     eso = 4 if w["out_f32"] else es
     fwd = (2 * R + 2 * G * N) * es + R * eso
     bwd = (2 * R + 2 * G * N) * es + R * eso + 2 * R * es + 2 * G * N * es
+    if w.get("z"):   # fwd also reads z; bwd also reads z and the saved out, and writes dz
+        fwd += R * es
+        bwd += 2 * R * es + R * es
     return fwd, bwd
 
 
@@ -82,7 +88,8 @@ def make_inputs(w, device, seed=0, dtype=torch.bfloat16):
     u = torch.randn(B, R, L, generator=gd, device=device).to(dtype)
     delta = (0.5 * torch.rand(B, R, L, generator=gd, device=device)).to(dtype)
     dout = torch.randn(B, R, L, generator=gd, device=device).to(torch.float32 if w["out_f32"] else dtype)
-    return dict(u=u, delta=delta, A=A.to(device), B=Bm, C=C, D=D.to(device), bias=bias.to(device), dout=dout)
+    z = torch.randn(B, R, L, generator=gd, device=device).to(dtype) if w.get("z") else None
+    return dict(u=u, delta=delta, A=A.to(device), B=Bm, C=C, D=D.to(device), bias=bias.to(device), dout=dout, z=z)
 
 
 class ClockSampler:
@@ -148,10 +155,12 @@ def run_device_steps(inp, steps, warmup, dist_grads=None):
     def one(ev=None):
         if ev:
             ev[0].record()
-        out, x, _ = scan_fwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], None, inp["bias"], True, out_f32)
+        z = inp.get("z")
+        out, x, _ = scan_fwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], z, inp["bias"], True, out_f32)
         if ev:
             ev[1].record()
-        g = scan_bwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], None, inp["bias"], inp["dout"], x, None, True)
+        g = scan_bwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], z, inp["bias"], inp["dout"], x,
+                     out if z is not None else None, True)
         if dist_grads is not None:
             dist_grads(g)
         if ev:
