@@ -12,11 +12,13 @@
 #include "scan_bwd_rows.cuh"
 #include "scan_fwd_rowsn.cuh"
 #include "scan_fwd_stream.cuh"
+#include "scan_fwd_chunks.cuh"
 
 namespace mia {
 template <typename T> cudaError_t launch_fwd_rows(const RowsArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_fwd_rowsn(const RowsNArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_fwd_stream(const StreamArgs &, int, bool, cudaStream_t);
+template <typename T> cudaError_t launch_fwd_chunks(const ChunkArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_rows(const RowsBwdArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_fwd_any(const ScanArgs &, int, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_any(const ScanArgs &, int, cudaStream_t);
@@ -277,6 +279,39 @@ bool plan_rows_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsArgs &
     return true;
 }
 
+// Chunk-parallel forward for long rows and few 32-row batches (scan_fwd_chunks.cuh): eligibility + argument block.
+bool plan_chunks_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::ChunkArgs &r, int &grid) {
+    const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
+    const int rpg = p.dim / p.n_groups;
+    if (p.dstate != 1 || p.z || p.delta_dim != p.dim || (rpg % 32) || (L % 4)) return false;
+    if (getenv("MIA_NO_ROWS_FWD") || getenv("MIA_NO_CHUNKS_FWD")) return false;   // debugging knobs
+    const int nch = (L + mia::kChunkTok - 1) / mia::kChunkTok;
+    if (nch < 2 || mia_ss_chunk_len(L) != mia::kChunkTok || ((L * es) % 16) || ((L * eo) % 16)) return false;
+    const int n_batches = p.batch * p.n_groups * (rpg / 32);
+    if (n_batches >= 4 * di.sms) return false;                 // enough rows: the serial row walk fills the machine
+    auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
+    if (!dense(p.u_batch_stride, p.u_d_stride) || !dense(p.delta_batch_stride, p.delta_d_stride) ||
+        !dense(p.out_batch_stride, p.out_d_stride)) return false;
+    if (p.A_d_stride != 1 && p.dim > 1) return false;
+    if (((uintptr_t)p.u | (uintptr_t)p.delta | (uintptr_t)p.out) & 15) return false;
+    memset(&r, 0, sizeof(r));
+    r.batch = p.batch; r.dim = p.dim; r.L = L; r.G = p.n_groups; r.rows_per_group = rpg; r.softplus = p.delta_softplus;
+    r.n_chunks = nch;
+    r.n_items = n_batches * nch;
+    r.tile_bytes = round_up(32 * (mia::kChunkTok * es + 16), 128);
+    r.off_bc32 = 2 * r.tile_bytes;
+    r.off_bar = r.off_bc32 + 2 * mia::kChunkTok * 4;
+    r.smem_bytes = r.off_bar + 128;
+    int per_sm = (227 * 1024) / (r.smem_bytes + 1024);
+    if (per_sm < 3) return false;
+    if (per_sm > 8) per_sm = 8;
+    r.u = p.u; r.delta = p.delta; r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.out = p.out; r.x = p.x;
+    r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride;
+    grid = di.sms * per_sm;
+    if (grid > r.n_items) grid = r.n_items;
+    return true;
+}
+
 // Streaming row-serial forward (scan_fwd_stream.cuh): eligibility + argument block.
 bool plan_stream_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::StreamArgs &r, int &grid) {
     const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
@@ -512,6 +547,20 @@ int mia_selective_scan_fwd(const mia_ss_params *pp, void *cuda_stream) {
     DeviceInfo di;
     if (int rc = device_info(di)) return rc;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
+    {
+        mia::ChunkArgs r;
+        int rgrid = 0;
+        if (plan_chunks_fwd(p, di, r, rgrid)) {
+            const bool of32 = p.otype == MIA_F32 && p.itype != MIA_F32;
+            const int rc = dispatch(p.itype, [&](auto *tag) {
+                using T = typename std::remove_pointer<decltype(tag)>::type;
+                return (int)mia::launch_fwd_chunks<T>(r, rgrid, of32, stream);
+            });
+            if (rc != 0) return fail(MIA_ECUDA, "selective_scan_fwd (chunk-parallel) launch: %s", cudaGetErrorString((cudaError_t)rc));
+            g_launches.fetch_add(3);
+            return MIA_OK;
+        }
+    }
     {
         mia::RowsArgs r;
         int rgrid = 0;
