@@ -32,9 +32,9 @@ WORKLOADS = {
     "ss2d_m6400_n16": dict(B=4, R=3072, G=4, L=6400, N=16, out_f32=False),
     "ss2d_m196_n1_o32": dict(B=64, R=3072, G=4, L=196, N=1, out_f32=True),
     "ss2d_m196_n16_o32": dict(B=64, R=3072, G=4, L=196, N=16, out_f32=True),
-    # the scan of one direction of the ARM / Vim mixer (MambaXray-VL-Base: d_model 768, expand 2 -> 1536 rows, one B/C
-    # group, d_state 16, z gate; arm/Finetuning/mamba_simple.py:693-704)
-    "arm_m196_n16_z": dict(B=64, R=1536, G=1, L=196, N=16, out_f32=False, z=True),
+    # one scan of the ARM mixer at BASELINE configs[1] (MambaXray-VL-Base, SURVEY 8: R = 768 rows, L = 197 = 14 x 14 + cls,
+    # one B/C group, d_state 16, z gate; arm/Finetuning/mamba_simple.py:693-704)
+    "arm_m197_n16_z": dict(B=64, R=768, G=1, L=197, N=16, out_f32=False, z=True),
 }
 DEFAULT = "ss2d_m196_n1"
 METRIC = "patch-tokens/sec SS2D fwd+bwd at L=196/6400 D=768; % HBM roofline"

@@ -348,7 +348,7 @@ bool plan_stream_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::StreamAr
 bool plan_rowsn_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsNArgs &r, int &grid) {
     const int es = esize(p.itype), L = p.seqlen, N = p.dstate;
     const int rpg = p.dim / p.n_groups;
-    if ((N != 16 && N != 8) || p.delta_dim != p.dim || (rpg % 32) || (L % 4)) return false;
+    if ((N != 16 && N != 8) || p.delta_dim != p.dim || (rpg % 32)) return false;
     if (getenv("MIA_NO_ROWS_FWD")) return false;                // debugging knob: force the warp-scan kernels
     if (mia_ss_num_chunks(L) != 1) return false;                // whole rows, one checkpoint
     auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };

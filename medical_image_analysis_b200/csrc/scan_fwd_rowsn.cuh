@@ -14,7 +14,8 @@
 // With the z gate of the mamba_ssm signature the z tile is a third tile per warp (2 warps per CTA), out_z = y silu(z)
 // overwrites it and leaves with a second bulk store; `out` (y before the gate) is still written: the backward needs it.
 // Preconditions (host-checked, otherwise the warp-scan kernels run): d_state == kN, delta per row, whole rows in
-// the tile (32 L es <= tile budget), rows contiguous, rows_per_group % 32 == 0, L % 4 == 0, 16-byte aligned tiles.
+// the tile (32 L es <= tile budget), rows contiguous, rows_per_group % 32 == 0, 16-byte aligned tiles; any L (odd L takes
+// an element-wise path for u / delta / z / y inside the same kernel).
 #pragma once
 #include <type_traits>
 
@@ -165,53 +166,76 @@ __global__ void __launch_bounds__(32 * kRowsNWarps) ss_fwd_rowsn_kernel(const __
         char *orow = kOutF32 ? (char *)a.out + (goff + (size_t)lane * L) * 4 : nullptr;
         char *ozrow = (kOutF32 && kHasZ) ? (char *)a.out_z + (goff + (size_t)lane * L) * 4 : nullptr;
 
+        // one token of this lane's row: all kN states advance, returns y (before the gate)
+        auto token = [&](const float m, const float uval, const int t) -> float {
+            const float2 m2 = splat2(m), mu2 = splat2(m * uval * kLn2);                // dl u = m u ln2
+            msum += m;
+            float2 Bv[kP], Cv[kP];
+            StateRow<T, kN>::ld(Bs + (size_t)t * kN, Bv);
+            StateRow<T, kN>::ld(Cs + (size_t)t * kN, Cv);
+            float2 yacc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int p = 0; p < kP; ++p) {
+                const float2 arg = mul2(m2, A2[p]);
+                const float2 av = make_float2(ex2f(arg.x), ex2f(arg.y));
+                h2[p] = fma2(av, h2[p], mul2(mu2, Bv[p]));
+                yacc = fma2(h2[p], Cv[p], yacc);
+            }
+            return fmaf(Dv, uval, yacc.x + yacc.y);
+        };
+        if ((L & 3) == 0) {
 #pragma unroll 1
-        for (int t = 0; t < L; t += 4) {
-            float2 dd[2], uu[2], y[2];
-            Quad<T>::ld(pd + t * es, dd);
-            Quad<T>::ld(pu + t * es, uu);
-            float mm[4], us[4] = {uu[0].x, uu[0].y, uu[1].x, uu[1].y}, ys[4];
-#pragma unroll
-            for (int qq = 0; qq < 2; ++qq) {
-                float2 m = fma2(dd[qq], kL2E, bl2);         // (delta + bias) * log2e
-                if (kSoftplus) {
-                    const float2 e = make_float2(ex2f(fminf(m.x, 120.f)), ex2f(fminf(m.y, 120.f)));
-                    const float2 sp = add2(e, kOne);
-                    m = make_float2(fmaxf(lg2f(sp.x), m.x), fmaxf(lg2f(sp.y), m.y));   // softplus * log2e
-                }
-                mm[2 * qq] = m.x; mm[2 * qq + 1] = m.y;
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 m2 = splat2(mm[i]), mu2 = splat2(mm[i] * us[i] * kLn2);   // dl u = m u ln2
-                msum += mm[i];
-                float2 Bv[kP], Cv[kP];
-                StateRow<T, kN>::ld(Bs + (size_t)(t + i) * kN, Bv);
-                StateRow<T, kN>::ld(Cs + (size_t)(t + i) * kN, Cv);
-                float2 yacc = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int p = 0; p < kP; ++p) {
-                    const float2 arg = mul2(m2, A2[p]);
-                    const float2 av = make_float2(ex2f(arg.x), ex2f(arg.y));
-                    h2[p] = fma2(av, h2[p], mul2(mu2, Bv[p]));
-                    yacc = fma2(h2[p], Cv[p], yacc);
-                }
-                ys[i] = fmaf(Dv, us[i], yacc.x + yacc.y);
-            }
-            y[0] = make_float2(ys[0], ys[1]);
-            y[1] = make_float2(ys[2], ys[3]);
-            if (kOutF32) *reinterpret_cast<float4 *>(orow + (size_t)t * 4) = make_float4(ys[0], ys[1], ys[2], ys[3]);
-            else Quad<T>::st(pu + t * es, y);                // y replaces u in place
-            if (kHasZ) {                                     // out_z = y * silu(z), computed from the unrounded y
-                float2 zz[2], yz[2];
-                Quad<T>::ld(pz + t * es, zz);
+            for (int t = 0; t < L; t += 4) {
+                float2 dd[2], uu[2], y[2];
+                Quad<T>::ld(pd + t * es, dd);
+                Quad<T>::ld(pu + t * es, uu);
+                float mm[4], us[4] = {uu[0].x, uu[0].y, uu[1].x, uu[1].y}, ys[4];
 #pragma unroll
                 for (int qq = 0; qq < 2; ++qq) {
-                    const float2 sz = make_float2(rcpf(1.f + ex2f(-zz[qq].x * kLog2e)), rcpf(1.f + ex2f(-zz[qq].y * kLog2e)));
-                    yz[qq] = mul2(mul2(y[qq], zz[qq]), sz);
+                    float2 m = fma2(dd[qq], kL2E, bl2);         // (delta + bias) * log2e
+                    if (kSoftplus) {
+                        const float2 e = make_float2(ex2f(fminf(m.x, 120.f)), ex2f(fminf(m.y, 120.f)));
+                        const float2 sp = add2(e, kOne);
+                        m = make_float2(fmaxf(lg2f(sp.x), m.x), fmaxf(lg2f(sp.y), m.y));   // softplus * log2e
+                    }
+                    mm[2 * qq] = m.x; mm[2 * qq + 1] = m.y;
                 }
-                if (kOutF32) *reinterpret_cast<float4 *>(ozrow + (size_t)t * 4) = make_float4(yz[0].x, yz[0].y, yz[1].x, yz[1].y);
-                else Quad<T>::st(pz + t * es, yz);           // out_z replaces z in place
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ys[i] = token(mm[i], us[i], t + i);
+                y[0] = make_float2(ys[0], ys[1]);
+                y[1] = make_float2(ys[2], ys[3]);
+                if (kOutF32) *reinterpret_cast<float4 *>(orow + (size_t)t * 4) = make_float4(ys[0], ys[1], ys[2], ys[3]);
+                else Quad<T>::st(pu + t * es, y);                // y replaces u in place
+                if (kHasZ) {                                     // out_z = y * silu(z), computed from the unrounded y
+                    float2 zz[2], yz[2];
+                    Quad<T>::ld(pz + t * es, zz);
+#pragma unroll
+                    for (int qq = 0; qq < 2; ++qq) {
+                        const float2 sz = make_float2(rcpf(1.f + ex2f(-zz[qq].x * kLog2e)), rcpf(1.f + ex2f(-zz[qq].y * kLog2e)));
+                        yz[qq] = mul2(mul2(y[qq], zz[qq]), sz);
+                    }
+                    if (kOutF32) *reinterpret_cast<float4 *>(ozrow + (size_t)t * 4) = make_float4(yz[0].x, yz[0].y, yz[1].x, yz[1].y);
+                    else Quad<T>::st(pz + t * es, yz);           // out_z replaces z in place
+                }
+            }
+        } else {
+            // odd lengths (L = 197 with the cls token of the ARM encoders): rows of the tile are only element-aligned, so u,
+            // delta, z and y move one element at a time -- two or three extra shared-memory instructions on ~100 per token
+#pragma unroll 1
+            for (int t = 0; t < L; ++t) {
+                const float dl = Cvt<T>::to_f(*reinterpret_cast<const raw *>(pd + t * es));
+                const float uval = Cvt<T>::to_f(*reinterpret_cast<const raw *>(pu + t * es));
+                float m = fmaf(dl, kLog2e, bl2.x);
+                if (kSoftplus) m = fmaxf(lg2f(1.f + ex2f(fminf(m, 120.f))), m);
+                const float yv = token(m, uval, t);
+                if (kOutF32) *reinterpret_cast<float *>(orow + (size_t)t * 4) = yv;
+                else *reinterpret_cast<raw *>(pu + t * es) = Cvt<T>::from_f(yv);
+                if (kHasZ) {
+                    const float zv = Cvt<T>::to_f(*reinterpret_cast<const raw *>(pz + t * es));
+                    const float yz = yv * zv * rcpf(1.f + ex2f(-zv * kLog2e));
+                    if (kOutF32) *reinterpret_cast<float *>(ozrow + (size_t)t * 4) = yz;
+                    else *reinterpret_cast<raw *>(pz + t * es) = Cvt<T>::from_f(yz);
+                }
             }
         }
         // checkpoint at the row end: (prod a_n, h_n) interleaved, prod a_n = 2^(A_n sum m)

@@ -104,7 +104,8 @@ def test_scan_parity_row_serial(shape, dtype, out_float):
 
 
 # d_state 16 / 8 shapes the row-serial forward for d_state > 1 takes (whole rows in one tile; the backward is the warp-scan one)
-ROWSN = [(2, 64, 196, 16, 2, 64), (1, 32, 4, 16, 1, 32), (2, 96, 100, 8, 3, 96), (1, 64, 208, 16, 1, 64), (3, 32, 52, 16, 1, 32)]
+ROWSN = [(2, 64, 196, 16, 2, 64), (1, 32, 4, 16, 1, 32), (2, 96, 100, 8, 3, 96), (1, 64, 208, 16, 1, 64), (3, 32, 52, 16, 1, 32),
+         (2, 64, 197, 16, 2, 64), (1, 32, 99, 8, 1, 32), (2, 32, 1, 16, 1, 32)]
 
 
 @pytest.mark.parametrize("shape", ROWSN, ids=[f"b{s[0]}d{s[1]}L{s[2]}N{s[3]}G{s[4]}" for s in ROWSN])
@@ -128,7 +129,7 @@ def test_scan_parity_flags(has_D, has_z, has_bias, softplus, dtype):
     _run_case(2, 16, 100, 4, 2, 16, has_D, has_z, has_bias, softplus, dtype, False, seed=3)
 
 
-@pytest.mark.parametrize("shape", [(2, 16, 196, 16, 1, 16), (1, 8, 300, 4, 2, 8), (2, 32, 197, 16, 1, 32), (2, 64, 196, 16, 2, 64), (1, 32, 100, 8, 1, 32)],
+@pytest.mark.parametrize("shape", [(2, 16, 196, 16, 1, 16), (1, 8, 300, 4, 2, 8), (2, 32, 197, 16, 1, 32), (2, 64, 196, 16, 2, 64), (1, 32, 100, 8, 1, 32), (2, 64, 197, 16, 1, 64)],
                          ids=lambda s: f"b{s[0]}d{s[1]}L{s[2]}N{s[3]}G{s[4]}")
 @pytest.mark.parametrize("dtype,out_float", [(torch.float32, False), (torch.bfloat16, False), (torch.bfloat16, True)], ids=["f32", "bf16", "bf16o32"])
 def test_scan_parity_z_gate_fast_backward(shape, dtype, out_float):
