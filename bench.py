@@ -152,7 +152,7 @@ def run_device_steps(inp, steps, warmup, dist_grads=None):
     from medical_image_analysis_b200 import scan_bwd, scan_fwd
     out_f32 = inp["dout"].dtype == torch.float32 and inp["u"].dtype != torch.float32
 
-    def one(ev=None):
+    def one(ev=None, last=False):
         if ev:
             ev[0].record()
         z = inp.get("z")
@@ -162,17 +162,17 @@ def run_device_steps(inp, steps, warmup, dist_grads=None):
         g = scan_bwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], z, inp["bias"], inp["dout"], x,
                      out if z is not None else None, True)
         if dist_grads is not None:
-            dist_grads(g)
+            dist_grads(g, last)
         if ev:
             ev[2].record()
         return out, g
 
-    for _ in range(warmup):
-        one()
+    for k in range(warmup):
+        one(None, k == warmup - 1)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
     torch.cuda.synchronize()
     for k in range(steps):
-        one(evs[k])
+        one(evs[k], k == steps - 1)
     torch.cuda.synchronize()
     total = evs[0][0].elapsed_time(evs[-1][2])
     fwd = sum(e[0].elapsed_time(e[1]) for e in evs) / steps
@@ -353,9 +353,21 @@ def main():
     inp = make_inputs(w, dev, seed=rank)
     dist_grads = None
     if world > 1:
-        def dist_grads(g):  # DDP's gradient step: all-reduce of the parameter gradients only
+        pending = []
+
+        def dist_grads(g, last=False):
+            """DDP's gradient step: one bucket with the parameter gradients (dA, dD, d_delta_bias), all-reduced
+            asynchronously on NCCL's stream so that it overlaps the next step's forward (as DDP overlaps its buckets with
+            the rest of the backward); the previous step's bucket is waited for first, the last one inside the timed region."""
+            for h in pending:
+                h.wait()
+            pending.clear()
             flat = torch.cat([g[2].flatten(), g[5], g[6]])
-            dist.all_reduce(flat)
+            h = dist.all_reduce(flat, async_op=True)
+            if last:
+                h.wait()
+            else:
+                pending.append(h)
     sampler = ClockSampler(local_rank)
     if world > 1:
         dist.barrier()
