@@ -401,7 +401,8 @@ bool plan_rows_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsBwdArg
     r.batch = p.batch; r.dim = p.dim; r.L = L; r.G = p.n_groups; r.rows_per_group = rpg; r.softplus = p.delta_softplus;
     r.n_chunks = nch;
     const int span = nch == 1 ? L : CH;                         // tokens of a row resident at a time
-    const int T0 = (span * 13 / 25) / 4 * 4;                    // 52 % of the chunk to the half that has no Gs to accumulate
+    r.t0_pct = getenv("MIA_T0_PCT") ? atoi(getenv("MIA_T0_PCT")) : 52;   // share of a chunk for the half that has no Gs to accumulate
+    const int T0 = (span * r.t0_pct / 100) / 4 * 4;
     const int longer = T0 > span - T0 ? T0 : span - T0;
     r.nblk = (longer + mia::kBlk - 1) / mia::kBlk;
     r.Lp = (span + mia::kBlk - 1) / mia::kBlk * mia::kBlk + mia::kBlk;

@@ -32,6 +32,7 @@ struct RowsBwdArgs {
     int batch, dim, L, G, rows_per_group;
     int softplus;
     int n_items, nblk, n_chunks;           // nblk: checkpoint slots per half of a chunk; n_chunks: 256-token chunks per row
+    int t0_pct;                            // percent of a chunk's tokens owned by warp 0
     int tile_bytes, tileo_bytes;            // one [32 x L] tile of u / delta, of dout
     int off_delta, off_dout, off_bc32, off_ck, off_xch, off_bar, smem_bytes;
     int Lp;                                 // L rounded up to kBlk (length of the fp32 B' and C rows)
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(64, 5) ss_bwd_rows_kernel(const __grid_constan
 
         for (int c = nch - 1; c >= 0; --c) {
             const int l0 = c * kRowsChunk, len = min(kRowsChunk, L - l0);
-            const int T0 = (len * 13 / 25) / 4 * 4;
+            const int T0 = (len * a.t0_pct / 100) / 4 * 4;
             const int tb = warp == 0 ? 0 : T0, tn = warp == 0 ? T0 : len - T0, tend = tb + tn;
             const int nb = (tn + kBlk - 1) / kBlk;
             const int nq_last = (tn - (nb - 1) * kBlk) / 4;              // quads of the half's last block
