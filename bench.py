@@ -251,6 +251,60 @@ def run_e2e_steps(w, inp, steps, warmup, n_slices=4):
     return e0.elapsed_time(e1), h2d, d2h
 
 
+def aux_kernels(dev, peak_gbs, n=20):
+    """The smaller kernels of the path: depth-wise causal conv1d + SiLU of the Mamba mixers and SS2D's
+    CrossScan / CrossMerge, timed as `n` back-to-back C-ABI launches on resident bf16 tensors (CUDA events), reported as
+    algorithmic GB/s (every tensor read or written once) and fraction of the measured HBM peak."""
+    from medical_image_analysis_b200 import _lib
+    L_ = _lib.lib()
+    st = torch.cuda.current_stream(dev).cuda_stream
+    out = []
+
+    def timed(fn):
+        for _ in range(3):
+            assert fn() == 0
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    B, D, L = 64, 1536, 196                                      # ARM mixer: d_inner 1536, 14 x 14 tokens
+    x = torch.randn(B, D, L, device=dev).bfloat16()
+    y, dy, dx = torch.empty_like(x), torch.randn_like(x), torch.empty_like(x)
+    w, b = torch.randn(D, 4, device=dev), torch.randn(D, device=dev)
+    dw, db = torch.empty_like(w), torch.empty_like(b)
+    nbytes = x.numel() * 2
+    t = timed(lambda: L_.mia_causal_conv1d_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), B, D, L, 4, 1, 2, D * L, L, D * L, L, st))
+    out.append({"kernel": "causal_conv1d_fwd (B=64, D=1536, L=196, k=4, silu, bf16)", "us": t * 1e3, "gbs": 2 * nbytes / t / 1e6})
+    t = timed(lambda: L_.mia_causal_conv1d_bwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), dy.data_ptr(), dx.data_ptr(), dw.data_ptr(),
+                                               db.data_ptr(), B, D, L, 4, 1, 2, D * L, L, D * L, L, D * L, L, st))
+    out.append({"kernel": "causal_conv1d_bwd (same shape)", "us": t * 1e3, "gbs": 3 * nbytes / t / 1e6})
+    B, C, H, W = 64, 768, 14, 14                                 # SS2D: d_inner 768, 14 x 14
+    xi = torch.randn(B, C, H, W, device=dev).bfloat16()
+    xs = torch.empty(B, 4, C, H * W, device=dev, dtype=torch.bfloat16)
+    yo = torch.empty(B, C, H * W, device=dev, dtype=torch.bfloat16)
+    nb = xi.numel() * 2
+    t = timed(lambda: L_.mia_cross_scan(xi.data_ptr(), xs.data_ptr(), B, C, H, W, 2, st))
+    out.append({"kernel": "cross_scan (B=64, C=768, 14x14, bf16)", "us": t * 1e3, "gbs": 5 * nb / t / 1e6})
+    t = timed(lambda: L_.mia_cross_merge(xs.data_ptr(), yo.data_ptr(), B, C, H, W, 2, st))
+    out.append({"kernel": "cross_merge (same shape)", "us": t * 1e3, "gbs": 5 * nb / t / 1e6})
+    w9, dw9 = torch.randn(C, 9, device=dev), torch.empty(C, 9, device=dev)
+    bc, dbc = torch.randn(C, device=dev), torch.empty(C, device=dev)
+    y2, dy2, dx2 = torch.empty_like(xi), torch.randn_like(xi), torch.empty_like(xi)
+    t = timed(lambda: L_.mia_dwconv2d_fwd(xi.data_ptr(), w9.data_ptr(), bc.data_ptr(), y2.data_ptr(), B, C, H, W, 1, 2, st))
+    out.append({"kernel": "dwconv2d_3x3_silu_fwd (B=64, C=768, 14x14, bf16)", "us": t * 1e3, "gbs": 2 * nb / t / 1e6})
+    t = timed(lambda: L_.mia_dwconv2d_bwd(xi.data_ptr(), w9.data_ptr(), bc.data_ptr(), dy2.data_ptr(), dx2.data_ptr(), dw9.data_ptr(),
+                                          dbc.data_ptr(), B, C, H, W, 1, 2, st))
+    out.append({"kernel": "dwconv2d_3x3_silu_bwd (same shape)", "us": t * 1e3, "gbs": 3 * nb / t / 1e6})
+    for o in out:
+        o["hbm_frac"] = o["gbs"] / peak_gbs
+    return out
+
+
 def cpu_reference_run(w, steps, warmup, budget_s=150.0):
     """The reference's own CPU algorithm (oracle/selective_scan_ref.py = restatement of selective_scan_ref +
     torch autograd, all host threads) on a BOUNDED sample of the workload: one image (B=1), and if K steps of
@@ -441,6 +495,10 @@ def main():
             except Exception as e:  # report, never hide
                 extras.append({"workload": name, "error": repr(e)})
         line["extra_workloads"] = extras
+        try:
+            line["aux_kernels"] = aux_kernels(dev, peak)
+        except Exception as e:  # report, never hide
+            line["aux_kernels"] = {"error": repr(e)}
 
     if not args.no_cpu:
         torch.set_num_threads(os.cpu_count() or 1)

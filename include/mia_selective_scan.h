@@ -137,6 +137,16 @@ int mia_causal_conv1d_bwd(const void *x, const float *weight, const float *bias,
                           void *cuda_stream);
 const char *mia_conv_last_error(void);
 
+/* Depth-wise 3x3 conv2d (stride 1, padding 1, + bias, + SiLU) of SS2D on channel-first activations:
+ * `self.act(self.conv2d(x))`, R2GenCSR/VMamba/classification/models/vmamba.py:574-582, 1120-1122.  x, y, dy, dx: (batch,
+ * channels, H, W) contiguous, H*W <= 16384; weight (channels, 9) and bias (channels, may be NULL) fp32.  bwd writes dx,
+ * dweight (channels, 9) and dbias (if not NULL) completely (deterministic, no atomics). */
+int mia_dwconv2d_fwd(const void *x, const float *weight, const float *bias, void *y, int batch, int channels, int H, int W, int silu,
+                     int dtype, void *cuda_stream);
+int mia_dwconv2d_bwd(const void *x, const float *weight, const float *bias, const void *dy, void *dx, float *dweight, float *dbias,
+                     int batch, int channels, int H, int W, int silu, int dtype, void *cuda_stream);
+const char *mia_dwconv2d_last_error(void);
+
 /* Number of selective-scan kernel launches issued by this library in this process since load (bench.py gpu_launches). */
 uint64_t mia_launch_count(void);
 

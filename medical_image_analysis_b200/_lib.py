@@ -71,6 +71,11 @@ def lib() -> ctypes.CDLL:
         L.mia_causal_conv1d_bwd.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ci, ci, ci, ci, ci, ci, ll, ll, ll, ll, ll, ll, _vp]
         L.mia_causal_conv1d_bwd.restype = ci
         L.mia_conv_last_error.restype = ctypes.c_char_p
+        L.mia_dwconv2d_fwd.argtypes = [_vp, _vp, _vp, _vp, ci, ci, ci, ci, ci, ci, _vp]
+        L.mia_dwconv2d_fwd.restype = ci
+        L.mia_dwconv2d_bwd.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ci, ci, ci, ci, ci, ci, _vp]
+        L.mia_dwconv2d_bwd.restype = ci
+        L.mia_dwconv2d_last_error.restype = ctypes.c_char_p
         if L.mia_abi_version() != 1:
             raise RuntimeError(f"libmia_scan.so ABI version {L.mia_abi_version()} != 1: rebuild it")
         _lib = L

@@ -67,12 +67,122 @@ __global__ void __launch_bounds__(kCsThreads) cross_merge_kernel(const typename 
     }
 }
 
+// ---- vectorised variants (L % 4 == 0, 4-element aligned tensors): 8- / 16-byte global accesses instead of one element per
+// thread; the gathers of the column-major and reversed orders stay element-wise, but in shared memory.
+constexpr int kPlanesVec = 8;
+
+template <typename T> struct Q4;                 // 4 consecutive elements as one vector
+template <> struct Q4<float> { using vec = uint4; };
+template <> struct Q4<__half> { using vec = uint2; };
+template <> struct Q4<__nv_bfloat16> { using vec = uint2; };
+
+template <typename T>
+__device__ __forceinline__ typename Q4<T>::vec pack4(typename mia::Cvt<T>::raw a, typename mia::Cvt<T>::raw b, typename mia::Cvt<T>::raw c,
+                                                     typename mia::Cvt<T>::raw d) {
+    if constexpr (sizeof(T) == 4) return make_uint4(a, b, c, d);
+    else return make_uint2((uint32_t)a | ((uint32_t)b << 16), (uint32_t)c | ((uint32_t)d << 16));
+}
+
+__device__ __forceinline__ int cs_div(int i, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)i, magic) : i; }
+
+template <typename T>
+__global__ void __launch_bounds__(kCsThreads) cross_scan_vec_kernel(const typename mia::Cvt<T>::raw *__restrict__ x,
+                                                                    typename mia::Cvt<T>::raw *__restrict__ xs, int n_planes, int C,
+                                                                    int H, int W, uint32_t magic_q, uint32_t magic_h, uint32_t magic_c) {
+    using raw = typename mia::Cvt<T>::raw;
+    using vec = typename Q4<T>::vec;
+    extern __shared__ __align__(16) char smem_raw[];
+    raw *s = reinterpret_cast<raw *>(smem_raw);
+    const int L = H * W, Q = L >> 2;
+    const int p0 = blockIdx.x * kPlanesVec, np = min(kPlanesVec, n_planes - p0);
+    {
+        const vec *gx = reinterpret_cast<const vec *>(x + (size_t)p0 * L);
+        vec *sv = reinterpret_cast<vec *>(s);
+        for (int i = threadIdx.x; i < np * Q; i += kCsThreads) sv[i] = gx[i];
+    }
+    __syncthreads();
+    const size_t kstep = (size_t)C * L;
+    for (int i = threadIdx.x; i < np * Q; i += kCsThreads) {
+        const int pl = cs_div(i, magic_q), q = i - pl * Q, l0 = 4 * q;
+        const int p = p0 + pl, b = cs_div(p, magic_c), c = p - b * C;
+        const raw *sp = s + pl * L;
+        raw t[4], r[4], tr[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int l = l0 + j, w = cs_div(l, magic_h), h = l - w * H;      // column-major position l holds x[h][w]
+            t[j] = sp[h * W + w];
+            const int lr = L - 1 - l, wr = cs_div(lr, magic_h), hr = lr - wr * H;
+            r[j] = sp[lr];
+            tr[j] = sp[hr * W + wr];
+        }
+        raw *o = xs + ((size_t)b * 4 * C + c) * L + l0;
+        *reinterpret_cast<vec *>(o) = *reinterpret_cast<const vec *>(sp + l0);
+        *reinterpret_cast<vec *>(o + kstep) = pack4<T>(t[0], t[1], t[2], t[3]);
+        *reinterpret_cast<vec *>(o + 2 * kstep) = pack4<T>(r[0], r[1], r[2], r[3]);
+        *reinterpret_cast<vec *>(o + 3 * kstep) = pack4<T>(tr[0], tr[1], tr[2], tr[3]);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCsThreads) cross_merge_vec_kernel(const typename mia::Cvt<T>::raw *__restrict__ ys,
+                                                                     typename mia::Cvt<T>::raw *__restrict__ y, int n_planes, int C,
+                                                                     int H, int W, uint32_t magic_q, uint32_t magic_w, uint32_t magic_c) {
+    using raw = typename mia::Cvt<T>::raw;
+    using vec = typename Q4<T>::vec;
+    extern __shared__ __align__(16) char smem_raw[];
+    raw *s = reinterpret_cast<raw *>(smem_raw);               // [plane][direction][L]
+    const int L = H * W, Q = L >> 2;
+    const int p0 = blockIdx.x * kPlanesVec, np = min(kPlanesVec, n_planes - p0);
+    const size_t kstep = (size_t)C * L;
+    for (int i = threadIdx.x; i < np * 4 * Q; i += kCsThreads) {
+        const int pd = cs_div(i, magic_q), q = i - pd * Q;      // pd = plane * 4 + direction
+        const int pl = pd >> 2, k = pd & 3;
+        const int p = p0 + pl, b = cs_div(p, magic_c), c = p - b * C;
+        reinterpret_cast<vec *>(s)[i] = reinterpret_cast<const vec *>(ys + ((size_t)b * 4 * C + c) * L + k * kstep)[q];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < np * Q; i += kCsThreads) {
+        const int pl = cs_div(i, magic_q), q = i - pl * Q, l0 = 4 * q;
+        const raw *sp = s + (size_t)pl * 4 * L;
+        raw o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int l = l0 + j, h = cs_div(l, magic_w), w = l - h * W, tl = w * H + h;   // x[h][w] sits at tl in the column-major orders
+            const float v = mia::Cvt<T>::to_f(sp[l]) + mia::Cvt<T>::to_f(sp[2 * L + (L - 1 - l)]) + mia::Cvt<T>::to_f(sp[L + tl]) +
+                            mia::Cvt<T>::to_f(sp[3 * L + (L - 1 - tl)]);
+            o[j] = mia::Cvt<T>::from_f(v);
+        }
+        *reinterpret_cast<vec *>(y + (size_t)(p0 + pl) * L + l0) = pack4<T>(o[0], o[1], o[2], o[3]);
+    }
+}
+
+uint32_t cs_magic(int d) { return d == 1 ? 0u : (uint32_t)((0x100000000ULL + (uint64_t)d - 1) / (uint64_t)d); }
+
 thread_local char g_cs_err[256] = "";
 
 template <typename T>
 int launch_cs(bool merge, const void *in, void *out, int B, int C, int H, int W, cudaStream_t stream) {
     using raw = typename mia::Cvt<T>::raw;
     const int n_planes = B * C, L = H * W;
+    const bool aligned = ((((uintptr_t)in | (uintptr_t)out) & (4 * sizeof(raw) - 1)) == 0);
+    const size_t vsmem = (size_t)kPlanesVec * L * sizeof(raw) * (merge ? 4 : 1);
+    if ((L % 4) == 0 && aligned && vsmem <= 200 * 1024 && (long long)kPlanesVec * L * L < (1LL << 32) / 4 &&
+        (long long)n_planes * C < (1LL << 32)) {   // ranges in which the multiply-high divisions are exact
+        const int grid = (n_planes + kPlanesVec - 1) / kPlanesVec;
+        cudaError_t e;
+        if (merge) {
+            auto k = &cross_merge_vec_kernel<T>;
+            if (vsmem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem)) != cudaSuccess) return MIA_ECUDA;
+            k<<<grid, kCsThreads, vsmem, stream>>>(reinterpret_cast<const raw *>(in), reinterpret_cast<raw *>(out), n_planes, C, H, W,
+                                                  cs_magic(L / 4), cs_magic(W), cs_magic(C));
+        } else {
+            auto k = &cross_scan_vec_kernel<T>;
+            if (vsmem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem)) != cudaSuccess) return MIA_ECUDA;
+            k<<<grid, kCsThreads, vsmem, stream>>>(reinterpret_cast<const raw *>(in), reinterpret_cast<raw *>(out), n_planes, C, H, W,
+                                                  cs_magic(L / 4), cs_magic(H), cs_magic(C));
+        }
+        return cudaGetLastError() == cudaSuccess ? MIA_OK : MIA_ECUDA;
+    }
     const size_t smem = (size_t)kPlanes * L * (merge ? sizeof(float) : sizeof(raw));
     if (smem > 200 * 1024) return MIA_EINVAL;
     const int grid = (n_planes + kPlanes - 1) / kPlanes;

@@ -34,6 +34,52 @@ def _cs_call(fn, src: torch.Tensor, dst: torch.Tensor, B: int, C: int, H: int, W
         _lib.check(fn(src.data_ptr(), dst.data_ptr(), B, C, H, W, _DT[src.dtype], stream), "cross scan/merge")
 
 
+class DWConv2dFn(torch.autograd.Function):
+    """Depth-wise 3x3 conv2d (+ bias, + SiLU) of SS2D through the C ABI (csrc/dwconv2d.cu); x (B, C, H, W) channel-first,
+    weight (C, 1, 3, 3) as held by nn.Conv2d(C, C, 3, padding=1, groups=C) (vmamba.py:574-582, 1120-1122)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x, weight, bias, silu):
+        if x.dim() != 4 or tuple(weight.shape) != (x.shape[1], 1, 3, 3):
+            raise RuntimeError("dwconv2d: x must be (B, C, H, W) and weight (C, 1, 3, 3)")
+        if not x.is_cuda:
+            raise RuntimeError("dwconv2d: the B200 build has no CPU path (x must be a CUDA tensor)")
+        x = x.contiguous()
+        w32 = weight.detach().float().reshape(-1, 9).contiguous()
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        y = torch.empty_like(x)
+        B, C, H, W = x.shape
+        rc = _lib.lib().mia_dwconv2d_fwd(x.data_ptr(), w32.data_ptr(), 0 if b32 is None else b32.data_ptr(), y.data_ptr(), B, C, H, W,
+                                         int(silu), _DT[x.dtype], torch.cuda.current_stream(x.device).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"dwconv2d_fwd: {_lib.lib().mia_dwconv2d_last_error().decode()} (code {rc})")
+        ctx.save_for_backward(x, w32, b32 if b32 is not None else w32.new_empty(0))
+        ctx.silu, ctx.has_bias, ctx.wdtype, ctx.bdtype = bool(silu), bias is not None, weight.dtype, None if bias is None else bias.dtype
+        return y
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        x, w32, b32 = ctx.saved_tensors
+        dy = dy.to(x.dtype).contiguous()
+        B, C, H, W = x.shape
+        dx = torch.empty_like(x)
+        dw = torch.empty_like(w32)
+        db = torch.empty(C, device=x.device, dtype=torch.float32) if ctx.has_bias else None
+        rc = _lib.lib().mia_dwconv2d_bwd(x.data_ptr(), w32.data_ptr(), b32.data_ptr() if ctx.has_bias else 0, dy.data_ptr(), dx.data_ptr(),
+                                         dw.data_ptr(), 0 if db is None else db.data_ptr(), B, C, H, W, int(ctx.silu), _DT[x.dtype],
+                                         torch.cuda.current_stream(x.device).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"dwconv2d_bwd: {_lib.lib().mia_dwconv2d_last_error().decode()} (code {rc})")
+        return dx, dw.view(C, 1, 3, 3).to(ctx.wdtype), (db.to(ctx.bdtype) if db is not None else None), None
+
+
+def dwconv2d_silu(x, conv: nn.Conv2d, silu: bool = True):
+    """`act(conv2d(x))` for SS2D's depth-wise 3x3 conv; anything else (other kernel sizes / strides) is not this op."""
+    return DWConv2dFn.apply(x, conv.weight, conv.bias, silu)
+
+
 def cross_scan_fwd(x: torch.Tensor) -> torch.Tensor:
     """(B, C, H, W) -> (B, 4, C, H*W): row-major, column-major and their reversals (vmamba.py:28-35)."""
     B, C, H, W = x.shape
@@ -303,9 +349,12 @@ class SS2D(nn.Module):
                 z = self.act(z)
         if not self.channel_first:
             x = x.permute(0, 3, 1, 2).contiguous()
-        if self.d_conv > 1:
-            x = self.conv2d(x)
-        x = self.act(x)
+        if self.d_conv == 3 and isinstance(self.act, nn.SiLU) and x.is_cuda and x.shape[-2] * x.shape[-1] <= 16384:
+            x = dwconv2d_silu(x, self.conv2d, True)      # depth-wise 3x3 conv + bias + SiLU in one kernel
+        else:
+            if self.d_conv > 1:
+                x = self.conv2d(x)
+            x = self.act(x)
         y = self.forward_core(x)
         if not self.disable_z:
             y = y * z
