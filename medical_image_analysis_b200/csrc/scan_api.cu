@@ -202,9 +202,7 @@ bool layout_smem(mia::ScanArgs &a, int es, int eso, bool bwd, int smem_max) {
     const int bars = round_up((2 * mia::kMaxStages + 2 * mia::kGroupStages) * 8, 128);
     const int carry = round_up(bwd ? (2 * a.RS * a.N + 2 * a.RS) * 4 : a.RS * a.N * 8, 128);
     const int red = bwd ? a.n_consumer_warps * 256 * 4 : 0;
-    // d_state > 1 fast backward (scan_bwd_fastn.cuh): the B / C chunk of all states once more as aligned fp32
-    const bool fastn = bwd && a.N > 1 && a.LPR == 32 && a.delta_ratio == 1;
-    const int bcf = fastn ? 2 * a.N * 256 * 4 : 0;
+    const int bcf = 0;   // (an fp32 copy of the B / C chunk for the d_state > 1 fast backward was tried and removed)
     const int fixed = mia::kGroupStages * a.gstage_bytes + bars + carry + red + bcf;
     int stages = (smem_max - fixed) / a.stage_bytes;
     if (stages > mia::kMaxStages) stages = mia::kMaxStages;

@@ -9,6 +9,8 @@
 //   * the sigmoid of the softplus derivative is rebuilt from m after the state loop (1 - 2^-m) instead of being held in
 //     8 registers across it;
 //   * (dA, dD, dbias) leave through the 6-shuffle warp_sum3 of the d_state = 1 path where possible.
+// (Pre-converting the B / C chunk to aligned fp32 in shared memory was tried and removed: it cut ~45 instructions per
+// (row, state) but cost a row stage and two consumer barriers per chunk, and the kernel got slower, not faster.)
 // dB / dC are still vector reductions into the L2-resident accumulator (red.global.add.v4.f32): shared-memory fp32
 // atomics are CAS loops on sm_100 (ATOMS.CAST.SPIN) and 2 x N x 256 register accumulators do not exist.
 #pragma once
@@ -75,20 +77,6 @@ __global__ void __launch_bounds__(kThreads, 1) ss_bwd_fastn_kernel(const __grid_
             const char *gC = (const char *)a.C + ((size_t)sc.b * a.C_bs + (size_t)sc.g * a.C_gs + l0) * es;
             const RowView vB = make_view(gs + a.goff_B, gB, a.B_ns, len, es, a.bc_pitch, a.flat_B);
             const RowView vC = make_view(gs + a.goff_C, gC, a.C_ns, len, es, a.bc_pitch, a.flat_C);
-            // B / C of this (segment, chunk) once more as aligned fp32, [tensor][state][half: tokens 0-3 / 4-7 of a lane][lane]
-            // float4s: the per-state loads of the row loop become four conflict-free LDS.128 without conversion or
-            // alignment dispatch.  One consumer barrier before (the previous chunk's readers are done) and one after.
-            float4 *bcf = reinterpret_cast<float4 *>(smem + a.off_bcf);
-            consumer_bar(NW * 32);
-            for (int idx = warp; idx < 2 * N; idx += NW) {
-                const int n = idx >> 1;
-                float2 v[4];
-                lds8v<T>(((idx & 1) ? vC : vB).row(n) + tok0 * es, v);
-                float4 *dst = bcf + (size_t)idx * 64;
-                dst[lane] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
-                dst[32 + lane] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
-            }
-            consumer_bar(NW * 32);
             const float *pA = reinterpret_cast<const float *>(gs + a.goff_A);
             const float *pD = reinterpret_cast<const float *>(gs + a.goff_D);
             const float *pbias = reinterpret_cast<const float *>(gs + a.goff_bias);
@@ -176,14 +164,8 @@ __global__ void __launch_bounds__(kThreads, 1) ss_bwd_fastn_kernel(const __grid_
                     for (int n = 0; n < N; ++n) {
                         const float Araw = pAr[n] * kLn2;       // the group stage holds A * log2e
                         float2 B2[4], C2[4], a2[4], ah2[4];
-                        {
-                            const float4 *src = bcf + (size_t)n * 128 + lane;
-                            const float4 b0 = src[0], b1 = src[32], c0 = src[64], c1 = src[96];
-                            B2[0] = make_float2(b0.x, b0.y); B2[1] = make_float2(b0.z, b0.w);
-                            B2[2] = make_float2(b1.x, b1.y); B2[3] = make_float2(b1.z, b1.w);
-                            C2[0] = make_float2(c0.x, c0.y); C2[1] = make_float2(c0.z, c0.w);
-                            C2[2] = make_float2(c1.x, c1.y); C2[3] = make_float2(c1.z, c1.w);
-                        }
+                        lds8v<T>(vB.row(n) + tok0 * es, B2);
+                        lds8v<T>(vC.row(n) + tok0 * es, C2);
                         // ---- forward recompute: lane aggregate, warp scan, per-token states
                         float pa = ex2f(msum * Araw), pb = 0.f;  // product of the lane's 8 a: one MUFU instead of 8 FMUL
 #pragma unroll
