@@ -26,7 +26,9 @@ import torch  # noqa: E402
 
 # name -> batch, rows, groups, L, d_state, out_f32 ("oflex": fp32 out / dout)
 WORKLOADS = {
-    "ss2d_m196_n1": dict(B=64, R=3072, G=4, L=196, N=1, out_f32=False),
+    # B = 148 = one image per SM: 148 x 96 = 14208 32-row batches = 12 full waves of the forward's 1184 resident warps
+    # (at B = 64 the 5.2 waves of the forward cost 6: -11 %; SURVEY 8d: "B chosen to fill the GPU (e.g. 64-256)")
+    "ss2d_m196_n1": dict(B=148, R=3072, G=4, L=196, N=1, out_f32=False),
     "ss2d_m196_n16": dict(B=64, R=3072, G=4, L=196, N=16, out_f32=False),
     "ss2d_m6400_n1": dict(B=4, R=3072, G=4, L=6400, N=1, out_f32=False),
     "ss2d_m6400_n16": dict(B=4, R=3072, G=4, L=6400, N=16, out_f32=False),
@@ -59,17 +61,21 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(kernel_key):
+def ncu_traffic(kernel_key, batch):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
-    capture of this same command (profiles/*_ncu_summary.json); None if no capture is committed."""
+    capture of this same command (profiles/*_ncu_summary.json); None if no capture is committed.  A capture taken at
+    another per-GPU batch is scaled linearly (the traffic of these kernels is proportional to the batch) and says so."""
     import glob
     for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json")), reverse=True):
         try:
-            d = json.load(open(f))[kernel_key]
+            full = json.load(open(f))
+            d = full[kernel_key]
             rd = float(d["dram__bytes_read.sum"].split()[0]); wr = float(d["dram__bytes_write.sum"].split()[0])
             unit = d["dram__bytes_read.sum"].split()[1]
             mult = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
-            return (rd + wr) * mult, os.path.basename(f)
+            cap_b = int(full.get("batch", batch))
+            src = os.path.basename(f) if cap_b == batch else f"{os.path.basename(f)} (captured at B={cap_b}, scaled by {batch}/{cap_b})"
+            return (rd + wr) * mult * batch / cap_b, src
         except Exception:
             continue
     return None, None
@@ -370,8 +376,11 @@ def main():
     ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of the workload")
     args = ap.parse_args()
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    if args.batch > 0:
+        w["B"] = args.batch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -465,7 +474,7 @@ def main():
     step_gbs = (value / world) * (fwd_b + bwd_b) / 1e9
     roofline = {"bound": "hbm", "kernel": "backward C-ABI call = %s + ss_finalize_kernel (timed together)" % ("ss_bwd_rows_kernel<bf16>" if w["N"] == 1 else "ss_bwd_kernel<bf16>"),
                 "achieved": bwd_gbs, "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak,
-                "traffic": (ncu_traffic("bwd")[0] if args.workload == DEFAULT else None), "traffic_source": ncu_traffic("bwd")[1],
+                "traffic": (ncu_traffic("bwd", w["B"])[0] if args.workload == DEFAULT else None), "traffic_source": ncu_traffic("bwd", w["B"])[1],
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": per_gpu_tokens * bwd_b,
                 "fwd_kernel": {"kernel": "forward C-ABI call = %s" % ("ss_fwd_rows_kernel<bf16>" if w["N"] == 1 else "ss_fwd_kernel<bf16>"), "achieved": fwd_gbs, "frac": fwd_gbs / peak,
                                "algorithmic_bytes_per_launch": per_gpu_tokens * fwd_b},

@@ -1,13 +1,14 @@
 """Condense ncu reports into the small text/CSV files committed under profiles/."""
 import collections, csv, json, re, subprocess, sys
 tag, fwd_rep, bwd_rep, launches = sys.argv[1:5]
+batch = int(sys.argv[5]) if len(sys.argv) > 5 else 64
 KEYS = ['gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
  'sm__throughput.avg.pct_of_peak_sustained_elapsed','smsp__issue_active.avg.pct_of_peak_sustained_active','smsp__inst_executed.sum',
  'launch__registers_per_thread','launch__grid_size','launch__block_size','launch__occupancy_limit_shared_mem','smsp__warps_active.avg.per_cycle_active',
  'smsp__warps_eligible.avg.per_cycle_active','sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
  'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active','sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
  'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum','l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum','lts__t_sector_hit_rate.pct']
-out = {}
+out = {'batch': batch}
 for name, rep in (('fwd', fwd_rep), ('bwd', bwd_rep)):
     raw = subprocess.run(['ncu','-i',rep,'--page','raw','--csv'],capture_output=True,text=True).stdout
     r = list(csv.reader(raw.splitlines())); h, u, v = r[0], r[1], r[2]
