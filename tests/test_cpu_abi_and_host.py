@@ -122,3 +122,14 @@ def test_causal_conv1d_has_no_cpu_path():
     conv = torch.nn.Conv1d(6, 6, 4, groups=6, padding=3)
     with pytest.raises(RuntimeError, match="no CPU path"):
         causal_conv1d_fn(torch.randn(2, 6, 20), conv.weight.squeeze(1), conv.bias, "silu")
+
+
+def test_dwconv2d_has_no_cpu_path():
+    """SS2D's depth-wise conv kernel (csrc/dwconv2d.cu) is CUDA-only as well: a CPU tensor must raise, not fall back."""
+    import pytest
+    from medical_image_analysis_b200.vmamba import DWConv2dFn
+    conv = torch.nn.Conv2d(4, 4, 3, padding=1, groups=4)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        DWConv2dFn.apply(torch.randn(1, 4, 5, 5), conv.weight, conv.bias, True)
+    with pytest.raises(RuntimeError, match="weight"):
+        DWConv2dFn.apply(torch.randn(1, 4, 5, 5), torch.randn(4, 1, 5, 5), None, True)
