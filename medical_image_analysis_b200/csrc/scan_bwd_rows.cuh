@@ -1,4 +1,4 @@
-// Backward selective scan, ROW-SERIAL path (d_state == 1, rows of at most one 256-token chunk): one LANE per row.
+// Backward selective scan, ROW-SERIAL path (d_state == 1): one LANE per row, two warps per [32 rows x chunk] tile set.
 //
 // A warp owns 32 consecutive rows of one (batch, group): lane r walks the tokens of row r serially, so the scan itself
 // costs one FMA per token (no shuffle scans, no idle lanes past the row end) and B[t], C[t] are shared-memory
@@ -14,8 +14,11 @@
 // ss_finalize_kernel (bit-reproducible, like the warp-scan path).
 //
 // Log2-domain algebra as in scan_bwd_fast.cuh: m = softplus(delta + bias) log2e, a = 2^(m A), B' = B ln2.
-// Preconditions (host-checked, otherwise the warp-scan kernels run): d_state == 1, delta per row, no z, L <= 256,
-// L % 4 == 0, rows_per_group % 32 == 0, dense 16-byte aligned u / delta / dout / du / ddelta.
+// A CTA is two warps that split every chunk in time (see ss_bwd_rows_kernel); rows longer than 256 tokens are walked
+// chunk by chunk from the end, the entering state coming from the forward's checkpoints x.
+// Preconditions (host-checked, otherwise the warp-scan kernels run): d_state == 1, delta per row, no z, L % 4 == 0,
+// rows_per_group % 32 == 0, dense 16-byte aligned u / delta / dout / du / ddelta; L > 256 additionally needs 16-byte
+// aligned row pieces and is only chosen while every 32-row batch gets a resident CTA.
 #pragma once
 #include <cstdio>
 #include <cstdlib>
