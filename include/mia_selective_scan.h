@@ -118,9 +118,11 @@ int mia_selective_scan_bwd(const mia_ss_params *p, void *cuda_stream);
 
 /* CrossScan / CrossMerge of SS2D (R2GenCSR/VMamba/classification/models/vmamba.py:25-67, csm_triton.py:163-235).
  * x, y: (batch, channels, H, W) contiguous; xs, ys: (batch, 4, channels, H*W) contiguous; same dtype in and out.
- * scan: xs[:,0] = row-major, xs[:,1] = column-major, xs[:,2:4] = their reversals.  merge = its adjoint (fp32 sum). */
+ * scan: xs[:,0] = row-major, xs[:,1] = column-major, xs[:,2:4] = their reversals.  merge = its adjoint (fp32 sum).
+ * Any H, W: planes are staged in shared memory while one fits (H W <= ~50 K elements), gathered directly beyond. */
 int mia_cross_scan(const void *x, void *xs, int batch, int channels, int H, int W, int dtype, void *cuda_stream);
 int mia_cross_merge(const void *ys, void *y, int batch, int channels, int H, int W, int dtype, void *cuda_stream);
+const char *mia_cs_last_error(void);   /* message of the last failed mia_cross_scan / mia_cross_merge on this thread */
 
 /* Depth-wise causal conv1d (+ bias, + SiLU) of the Mamba mixers: y[b, d, t] = act(bias[d] + sum_k w[d, k] x[b, d, t - (K-1) + k]).
  * Replaces causal_conv1d.causal_conv1d_fn (un-vendored; call sites arm/Finetuning/mamba_simple.py:676-681 of the three ARM sub-projects) == the in-repo

@@ -65,6 +65,7 @@ def lib() -> ctypes.CDLL:
         for fn in (L.mia_cross_scan, L.mia_cross_merge):
             fn.argtypes = [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]
             fn.restype = ctypes.c_int
+        L.mia_cs_last_error.restype = ctypes.c_char_p
         ll, ci = ctypes.c_longlong, ctypes.c_int
         L.mia_causal_conv1d_fwd.argtypes = [_vp, _vp, _vp, _vp, ci, ci, ci, ci, ci, ci, ll, ll, ll, ll, _vp]
         L.mia_causal_conv1d_fwd.restype = ci

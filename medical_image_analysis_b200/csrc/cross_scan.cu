@@ -7,23 +7,25 @@
 // 4 reads + 1 write (merge) per element.
 #include <cuda_runtime.h>
 
+#include <cstdio>
+
 #include "../../include/mia_selective_scan.h"
 #include "scan_common.cuh"
 
 namespace {
 
-constexpr int kPlanes = 4;      // planes per CTA
+constexpr int kPlanes = 4;      // planes per CTA (fewer when a plane is large: see launch_cs)
 constexpr int kCsThreads = 256;
 
 template <typename T>
 __global__ void __launch_bounds__(kCsThreads) cross_scan_kernel(const typename mia::Cvt<T>::raw *__restrict__ x,
                                                                 typename mia::Cvt<T>::raw *__restrict__ xs, int n_planes, int C,
-                                                                int H, int W) {
+                                                                int H, int W, int planes) {
     using raw = typename mia::Cvt<T>::raw;
     extern __shared__ __align__(16) char smem_raw[];
     raw *s = reinterpret_cast<raw *>(smem_raw);
     const int L = H * W;
-    const int p0 = blockIdx.x * kPlanes, np = min(kPlanes, n_planes - p0);
+    const int p0 = blockIdx.x * planes, np = min(planes, n_planes - p0);
     for (int i = threadIdx.x; i < np * L; i += kCsThreads) s[i] = x[(size_t)p0 * L + i];
     __syncthreads();
     for (int i = threadIdx.x; i < np * L; i += kCsThreads) {
@@ -43,12 +45,12 @@ __global__ void __launch_bounds__(kCsThreads) cross_scan_kernel(const typename m
 template <typename T>
 __global__ void __launch_bounds__(kCsThreads) cross_merge_kernel(const typename mia::Cvt<T>::raw *__restrict__ ys,
                                                                  typename mia::Cvt<T>::raw *__restrict__ y, int n_planes, int C,
-                                                                 int H, int W) {
+                                                                 int H, int W, int planes) {
     using raw = typename mia::Cvt<T>::raw;
     extern __shared__ __align__(16) char smem_raw[];
     float *t = reinterpret_cast<float *>(smem_raw);          // column-major partial: ys1 + flip(ys3)
     const int L = H * W;
-    const int p0 = blockIdx.x * kPlanes, np = min(kPlanes, n_planes - p0);
+    const int p0 = blockIdx.x * planes, np = min(planes, n_planes - p0);
     const size_t kstep = (size_t)C * L;
     for (int i = threadIdx.x; i < np * L; i += kCsThreads) {
         const int pl = i / L, l = i - pl * L;
@@ -88,13 +90,13 @@ __device__ __forceinline__ int cs_div(int i, uint32_t magic) { return magic ? (i
 template <typename T>
 __global__ void __launch_bounds__(kCsThreads) cross_scan_vec_kernel(const typename mia::Cvt<T>::raw *__restrict__ x,
                                                                     typename mia::Cvt<T>::raw *__restrict__ xs, int n_planes, int C,
-                                                                    int H, int W, uint32_t magic_q, uint32_t magic_h, uint32_t magic_c) {
+                                                                    int H, int W, uint32_t magic_q, uint32_t magic_h, uint32_t magic_c, int planes) {
     using raw = typename mia::Cvt<T>::raw;
     using vec = typename Q4<T>::vec;
     extern __shared__ __align__(16) char smem_raw[];
     raw *s = reinterpret_cast<raw *>(smem_raw);
     const int L = H * W, Q = L >> 2;
-    const int p0 = blockIdx.x * kPlanesVec, np = min(kPlanesVec, n_planes - p0);
+    const int p0 = blockIdx.x * planes, np = min(planes, n_planes - p0);
     {
         const vec *gx = reinterpret_cast<const vec *>(x + (size_t)p0 * L);
         vec *sv = reinterpret_cast<vec *>(s);
@@ -126,13 +128,13 @@ __global__ void __launch_bounds__(kCsThreads) cross_scan_vec_kernel(const typena
 template <typename T>
 __global__ void __launch_bounds__(kCsThreads) cross_merge_vec_kernel(const typename mia::Cvt<T>::raw *__restrict__ ys,
                                                                      typename mia::Cvt<T>::raw *__restrict__ y, int n_planes, int C,
-                                                                     int H, int W, uint32_t magic_q, uint32_t magic_w, uint32_t magic_c) {
+                                                                     int H, int W, uint32_t magic_q, uint32_t magic_w, uint32_t magic_c, int planes) {
     using raw = typename mia::Cvt<T>::raw;
     using vec = typename Q4<T>::vec;
     extern __shared__ __align__(16) char smem_raw[];
     raw *s = reinterpret_cast<raw *>(smem_raw);               // [plane][direction][L]
     const int L = H * W, Q = L >> 2;
-    const int p0 = blockIdx.x * kPlanesVec, np = min(kPlanesVec, n_planes - p0);
+    const int p0 = blockIdx.x * planes, np = min(planes, n_planes - p0);
     const size_t kstep = (size_t)C * L;
     for (int i = threadIdx.x; i < np * 4 * Q; i += kCsThreads) {
         const int pd = cs_div(i, magic_q), q = i - pd * Q;      // pd = plane * 4 + direction
@@ -156,57 +158,127 @@ __global__ void __launch_bounds__(kCsThreads) cross_merge_vec_kernel(const typen
     }
 }
 
+// Planes too large for shared memory (H W > ~50 K elements): straight gathers from global memory, one element per thread.
+// The column-major orders are strided reads (scan) / reads of two strided tensors (merge); correct for any size.
+template <typename T>
+__global__ void __launch_bounds__(kCsThreads) cross_scan_direct_kernel(const typename mia::Cvt<T>::raw *__restrict__ x,
+                                                                       typename mia::Cvt<T>::raw *__restrict__ xs, long long total, int C,
+                                                                       int H, int W) {
+    using raw = typename mia::Cvt<T>::raw;
+    const int L = H * W;
+    const size_t kstep = (size_t)C * L;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / L;
+        const int l = (int)(i - p * L);
+        const int b = (int)(p / C), c = (int)(p - (long long)b * C);
+        const raw *src = x + (size_t)p * L;
+        const raw v = src[l], vt = src[(l % H) * W + l / H];
+        raw *o = xs + ((size_t)b * 4 * C + c) * L;
+        o[l] = v;
+        o[kstep + l] = vt;
+        o[2 * kstep + (L - 1 - l)] = v;
+        o[3 * kstep + (L - 1 - l)] = vt;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCsThreads) cross_merge_direct_kernel(const typename mia::Cvt<T>::raw *__restrict__ ys,
+                                                                        typename mia::Cvt<T>::raw *__restrict__ y, long long total, int C,
+                                                                        int H, int W) {
+    using raw = typename mia::Cvt<T>::raw;
+    const int L = H * W;
+    const size_t kstep = (size_t)C * L;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / L;
+        const int l = (int)(i - p * L);
+        const int b = (int)(p / C), c = (int)(p - (long long)b * C);
+        const raw *in = ys + ((size_t)b * 4 * C + c) * L;
+        const int h = l / W, w = l - h * W, tl = w * H + h;
+        const float v = mia::Cvt<T>::to_f(in[l]) + mia::Cvt<T>::to_f(in[2 * kstep + (L - 1 - l)]) + mia::Cvt<T>::to_f(in[kstep + tl]) +
+                        mia::Cvt<T>::to_f(in[3 * kstep + (L - 1 - tl)]);
+        y[(size_t)p * L + l] = mia::Cvt<T>::from_f(v);
+    }
+}
+
 uint32_t cs_magic(int d) { return d == 1 ? 0u : (uint32_t)((0x100000000ULL + (uint64_t)d - 1) / (uint64_t)d); }
 
 thread_local char g_cs_err[256] = "";
+int cs_fail(int code, const char *msg) { snprintf(g_cs_err, sizeof(g_cs_err), "%s", msg); return code; }
+int cs_cuda(const char *what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return MIA_OK;
+    snprintf(g_cs_err, sizeof(g_cs_err), "%s: %s", what, cudaGetErrorString(e));
+    return MIA_ECUDA;
+}
+
+constexpr size_t kCsSmemMax = 200 * 1024;
 
 template <typename T>
 int launch_cs(bool merge, const void *in, void *out, int B, int C, int H, int W, cudaStream_t stream) {
     using raw = typename mia::Cvt<T>::raw;
     const int n_planes = B * C, L = H * W;
     const bool aligned = ((((uintptr_t)in | (uintptr_t)out) & (4 * sizeof(raw) - 1)) == 0);
-    const size_t vsmem = (size_t)kPlanesVec * L * sizeof(raw) * (merge ? 4 : 1);
-    if ((L % 4) == 0 && aligned && vsmem <= 200 * 1024 && (long long)kPlanesVec * L * L < (1LL << 32) / 4 &&
+    // planes per CTA: as many as fit (8 for the 14 x 14 ... 56 x 56 maps of the models, fewer for large maps)
+    const size_t vplane = (size_t)L * sizeof(raw) * (merge ? 4 : 1);
+    int vplanes = (int)(kCsSmemMax / vplane);
+    if (vplanes > kPlanesVec) vplanes = kPlanesVec;
+    if ((L % 4) == 0 && aligned && vplanes >= 1 && (long long)vplanes * L * L < (1LL << 32) / 4 &&
         (long long)n_planes * C < (1LL << 32)) {   // ranges in which the multiply-high divisions are exact
-        const int grid = (n_planes + kPlanesVec - 1) / kPlanesVec;
-        cudaError_t e;
+        const size_t vsmem = vplane * vplanes;
+        const int grid = (n_planes + vplanes - 1) / vplanes;
         if (merge) {
             auto k = &cross_merge_vec_kernel<T>;
-            if (vsmem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem)) != cudaSuccess) return MIA_ECUDA;
+            if (vsmem > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem) != cudaSuccess)
+                return cs_cuda("cross_merge: cudaFuncSetAttribute");
             k<<<grid, kCsThreads, vsmem, stream>>>(reinterpret_cast<const raw *>(in), reinterpret_cast<raw *>(out), n_planes, C, H, W,
-                                                  cs_magic(L / 4), cs_magic(W), cs_magic(C));
+                                                  cs_magic(L / 4), cs_magic(W), cs_magic(C), vplanes);
         } else {
             auto k = &cross_scan_vec_kernel<T>;
-            if (vsmem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem)) != cudaSuccess) return MIA_ECUDA;
+            if (vsmem > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem) != cudaSuccess)
+                return cs_cuda("cross_scan: cudaFuncSetAttribute");
             k<<<grid, kCsThreads, vsmem, stream>>>(reinterpret_cast<const raw *>(in), reinterpret_cast<raw *>(out), n_planes, C, H, W,
-                                                  cs_magic(L / 4), cs_magic(H), cs_magic(C));
+                                                  cs_magic(L / 4), cs_magic(H), cs_magic(C), vplanes);
         }
-        return cudaGetLastError() == cudaSuccess ? MIA_OK : MIA_ECUDA;
+        return cs_cuda(merge ? "cross_merge launch" : "cross_scan launch");
     }
-    const size_t smem = (size_t)kPlanes * L * (merge ? sizeof(float) : sizeof(raw));
-    if (smem > 200 * 1024) return MIA_EINVAL;
-    const int grid = (n_planes + kPlanes - 1) / kPlanes;
-    cudaError_t e;
-    if (merge) {
-        auto k = &cross_merge_kernel<T>;
-        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return MIA_ECUDA;
-        k<<<grid, kCsThreads, smem, stream>>>(reinterpret_cast<const raw *>(in), reinterpret_cast<raw *>(out), n_planes, C, H, W);
-    } else {
-        auto k = &cross_scan_kernel<T>;
-        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return MIA_ECUDA;
-        k<<<grid, kCsThreads, smem, stream>>>(reinterpret_cast<const raw *>(in), reinterpret_cast<raw *>(out), n_planes, C, H, W);
+    const size_t plane = (size_t)L * (merge ? sizeof(float) : sizeof(raw));
+    int planes = (int)(kCsSmemMax / plane);
+    if (planes > kPlanes) planes = kPlanes;
+    if (planes >= 1) {
+        const size_t smem = plane * planes;
+        const int grid = (n_planes + planes - 1) / planes;
+        if (merge) {
+            auto k = &cross_merge_kernel<T>;
+            if (smem > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return cs_cuda("cross_merge: cudaFuncSetAttribute");
+            k<<<grid, kCsThreads, smem, stream>>>(reinterpret_cast<const raw *>(in), reinterpret_cast<raw *>(out), n_planes, C, H, W, planes);
+        } else {
+            auto k = &cross_scan_kernel<T>;
+            if (smem > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return cs_cuda("cross_scan: cudaFuncSetAttribute");
+            k<<<grid, kCsThreads, smem, stream>>>(reinterpret_cast<const raw *>(in), reinterpret_cast<raw *>(out), n_planes, C, H, W, planes);
+        }
+        return cs_cuda(merge ? "cross_merge launch" : "cross_scan launch");
     }
-    return cudaGetLastError() == cudaSuccess ? MIA_OK : MIA_ECUDA;
+    // a single plane exceeds shared memory: direct gathers
+    const long long total = (long long)n_planes * L;
+    long long blocks = (total + kCsThreads - 1) / kCsThreads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (merge) cross_merge_direct_kernel<T><<<(int)blocks, kCsThreads, 0, stream>>>(reinterpret_cast<const raw *>(in), reinterpret_cast<raw *>(out), total, C, H, W);
+    else cross_scan_direct_kernel<T><<<(int)blocks, kCsThreads, 0, stream>>>(reinterpret_cast<const raw *>(in), reinterpret_cast<raw *>(out), total, C, H, W);
+    return cs_cuda(merge ? "cross_merge (direct) launch" : "cross_scan (direct) launch");
 }
 
 int cs_dispatch(bool merge, const void *in, void *out, int B, int C, int H, int W, int dtype, void *stream) {
-    if (!in || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return MIA_EINVAL;
+    if (!in || !out) return cs_fail(MIA_EINVAL, "cross scan / merge: null pointer");
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return cs_fail(MIA_EINVAL, "cross scan / merge: empty or negative size");
+    if ((long long)H * W > (1LL << 30)) return cs_fail(MIA_EINVAL, "cross scan / merge: H * W too large");
     cudaStream_t st = (cudaStream_t)stream;
     switch (dtype) {
         case MIA_F32: return launch_cs<float>(merge, in, out, B, C, H, W, st);
         case MIA_F16: return launch_cs<__half>(merge, in, out, B, C, H, W, st);
         case MIA_BF16: return launch_cs<__nv_bfloat16>(merge, in, out, B, C, H, W, st);
-        default: return MIA_EINVAL;
+        default: return cs_fail(MIA_EINVAL, "cross scan / merge: dtype must be MIA_F32, MIA_F16 or MIA_BF16");
     }
 }
 
@@ -219,4 +291,5 @@ int mia_cross_scan(const void *x, void *xs, int batch, int channels, int H, int 
 int mia_cross_merge(const void *ys, void *y, int batch, int channels, int H, int W, int dtype, void *cuda_stream) {
     return cs_dispatch(true, ys, y, batch, channels, H, W, dtype, cuda_stream);
 }
+const char *mia_cs_last_error(void) { return g_cs_err; }
 }

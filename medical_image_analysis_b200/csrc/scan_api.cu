@@ -10,6 +10,7 @@
 #include "../../include/mia_selective_scan.h"
 #include "scan_common.cuh"
 #include "scan_bwd_rows.cuh"
+#include "scan_bwd_rowsn.cuh"
 #include "scan_fwd_rowsn.cuh"
 #include "scan_fwd_stream.cuh"
 #include "scan_fwd_chunks.cuh"
@@ -20,6 +21,7 @@ template <typename T> cudaError_t launch_fwd_rowsn(const RowsNArgs &, int, bool,
 template <typename T> cudaError_t launch_fwd_stream(const StreamArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_fwd_chunks(const ChunkArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_rows(const RowsBwdArgs &, int, bool, cudaStream_t);
+template <typename T> cudaError_t launch_bwd_rowsn(const RowsNBwdArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_fwd_any(const ScanArgs &, int, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_any(const ScanArgs &, int, cudaStream_t);
 }  // namespace mia
@@ -41,6 +43,16 @@ int fail(int code, const char *fmt, ...) {
     do { if (!(cond)) return fail(MIA_EINVAL, __VA_ARGS__); } while (0)
 #define MIA_CUDA(expr) \
     do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return fail(MIA_ECUDA, "%s: %s", #expr, cudaGetErrorString(e__)); } while (0)
+
+// Debugging knobs (force a kernel family, move the half split) exist only in -DMIA_DEBUG builds; the release library
+// reads no environment variable and has no mode that alters results.
+#ifdef MIA_DEBUG
+bool dbg_knob(const char *name) { return getenv(name) != nullptr; }
+int dbg_int(const char *name, int dflt) { const char *v = getenv(name); return v ? atoi(v) : dflt; }
+#else
+constexpr bool dbg_knob(const char *) { return false; }
+constexpr int dbg_int(const char *, int dflt) { return dflt; }
+#endif
 
 int esize(int dt) { return dt == MIA_F32 ? 4 : 2; }
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -117,7 +129,24 @@ Plan make_plan(const mia_ss_params &p, int sms, bool bwd) {
     return pl;
 }
 
-WorkspaceLayout workspace_layout(const mia_ss_params &p, const Plan &pl) {
+// Work split of the deterministic d_state 16 backward (scan_bwd_rowsn.cuh): sizes only, shared by the workspace query and
+// the launch.  Returns false when the shape is not one it takes.
+struct RowsNSplit { int n_oct, oct_per_cta, oct_per_group, grid, max_parts; };
+bool rowsn_bwd_split(const mia_ss_params &p, int sms, int ctas_per_sm, RowsNSplit &sp) {
+    const int rpg = p.dim / p.n_groups;
+    if (p.dstate != 16 || p.delta_dim != p.dim || p.seqlen > 256 || (rpg % mia::kRnOct)) return false;
+    sp.n_oct = (int)((long long)p.batch * p.dim / mia::kRnOct);
+    sp.oct_per_group = rpg / mia::kRnOct;
+    const int slots = sms * ctas_per_sm;
+    sp.oct_per_cta = (sp.n_oct + slots - 1) / slots;
+    sp.grid = (sp.n_oct + sp.oct_per_cta - 1) / sp.oct_per_cta;
+    sp.max_parts = (sp.oct_per_group + sp.oct_per_cta - 2) / sp.oct_per_cta + 1;   // CTAs a group's octets can straddle
+    return true;
+}
+constexpr int kRowsNCtasPerSm = 3;   // the split (hence the partial layout) is fixed at 3 CTAs per SM: launching fewer
+                                     // resident CTAs (z gate, fp32) only queues them
+
+WorkspaceLayout workspace_layout(const mia_ss_params &p, const Plan &pl, int sms) {
     WorkspaceLayout w;
     auto take = [&](size_t nfloat) { size_t off = w.total; w.total += (nfloat * 4 + 255) / 256 * 256; return off; };
     w.bc_atomic = p.dstate > 1;
@@ -130,6 +159,11 @@ WorkspaceLayout workspace_layout(const mia_ss_params &p, const Plan &pl) {
     const size_t row_items = (p.dstate == 1 && rpg % 32 == 0) ? (size_t)p.batch * p.n_groups * (rpg / 32) : 0;
     const size_t parts = row_items > (size_t)pl.n_seg ? row_items : (size_t)pl.n_seg;
     size_t nacc = w.bc_atomic ? (size_t)p.batch * p.n_groups * p.dstate * ((p.seqlen + 3) & ~3) : parts * p.dstate * p.seqlen;
+    RowsNSplit rs;
+    if (rowsn_bwd_split(p, sms, kRowsNCtasPerSm, rs)) {   // whichever d_state 16 kernel runs (it depends on strides), its buffer fits
+        const size_t need = (size_t)p.batch * p.n_groups * rs.max_parts * p.dstate * p.seqlen;
+        if (need > nacc) nacc = need;
+    }
     w.acc_dB = take(nacc);
     w.acc_dC = take(nacc);
     w.acc_bytes = nacc * 4;
@@ -137,17 +171,22 @@ WorkspaceLayout workspace_layout(const mia_ss_params &p, const Plan &pl) {
     return w;
 }
 
-int validate_common(const mia_ss_params &p) {
+int validate_sizes(const mia_ss_params &p) {
     MIA_CHECK(p.itype == MIA_F32 || p.itype == MIA_F16 || p.itype == MIA_BF16, "u must be float32, float16 or bfloat16");
     MIA_CHECK(p.otype == p.itype || p.otype == MIA_F32, "out/dout dtype must be the input dtype or float32");
     MIA_CHECK(p.batch > 0 && p.dim > 0 && p.seqlen > 0 && p.dstate > 0 && p.n_groups > 0 && p.delta_dim > 0, "empty or negative size");
     MIA_CHECK(p.dim % p.n_groups == 0, "dims should be dividable by n_groups");
     MIA_CHECK(p.dim % p.delta_dim == 0, "dims should be dividable by delta_dim");
     MIA_CHECK(p.dstate <= 256, "selective_scan only supports state dimension <= 256");
+    MIA_CHECK((long long)p.batch * p.dim < (1LL << 31) / 2, "batch*dim too large");
+    return MIA_OK;
+}
+
+int validate_common(const mia_ss_params &p) {
+    if (int rc = validate_sizes(p)) return rc;
     MIA_CHECK(p.u && p.delta && p.A && p.B && p.C, "u, delta, A, B, C must not be null");
     MIA_CHECK(p.n_chunks == mia_ss_num_chunks(p.seqlen), "x must have %d chunks for seqlen %d (got %d)", mia_ss_num_chunks(p.seqlen),
               p.seqlen, p.n_chunks);
-    MIA_CHECK((long long)p.batch * p.dim < (1LL << 31) / 2, "batch*dim too large");
     return MIA_OK;
 }
 
@@ -246,7 +285,7 @@ bool plan_rows_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsArgs &
     const int es = esize(p.itype), L = p.seqlen;
     const int rpg = p.dim / p.n_groups;
     if (p.dstate != 1 || p.z || p.delta_dim != p.dim || (rpg % 32) || (L % 4)) return false;
-    if (getenv("MIA_NO_ROWS_FWD")) return false;                // debugging knob: force the warp-scan kernels
+    if (dbg_knob("MIA_NO_ROWS_FWD")) return false;
     auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
     if (!dense(p.u_batch_stride, p.u_d_stride) || !dense(p.delta_batch_stride, p.delta_d_stride) ||
         !dense(p.out_batch_stride, p.out_d_stride)) return false;
@@ -282,7 +321,7 @@ bool plan_chunks_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::ChunkArg
     const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
     const int rpg = p.dim / p.n_groups;
     if (p.dstate != 1 || p.z || p.delta_dim != p.dim || (rpg % 32) || (L % 4)) return false;
-    if (getenv("MIA_NO_ROWS_FWD") || getenv("MIA_NO_CHUNKS_FWD")) return false;   // debugging knobs
+    if (dbg_knob("MIA_NO_ROWS_FWD") || dbg_knob("MIA_NO_CHUNKS_FWD")) return false;
     const int nch = (L + mia::kChunkTok - 1) / mia::kChunkTok;
     if (nch < 2 || mia_ss_chunk_len(L) != mia::kChunkTok || ((L * es) % 16) || ((L * eo) % 16)) return false;
     const int n_batches = p.batch * p.n_groups * (rpg / 32);
@@ -315,7 +354,7 @@ bool plan_stream_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::StreamAr
     const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
     const int rpg = p.dim / p.n_groups;
     if (p.dstate != 1 || p.z || p.delta_dim != p.dim || (rpg % 32) || (L % 4)) return false;
-    if (getenv("MIA_NO_ROWS_FWD") || getenv("MIA_NO_STREAM_FWD")) return false;   // debugging knobs
+    if (dbg_knob("MIA_NO_ROWS_FWD") || dbg_knob("MIA_NO_STREAM_FWD")) return false;
     auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
     if (!dense(p.u_batch_stride, p.u_d_stride) || !dense(p.delta_batch_stride, p.delta_d_stride) ||
         !dense(p.out_batch_stride, p.out_d_stride)) return false;
@@ -347,7 +386,7 @@ bool plan_rowsn_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsNArgs
     const int es = esize(p.itype), L = p.seqlen, N = p.dstate;
     const int rpg = p.dim / p.n_groups;
     if ((N != 16 && N != 8) || p.delta_dim != p.dim || (rpg % 32)) return false;
-    if (getenv("MIA_NO_ROWS_FWD")) return false;                // debugging knob: force the warp-scan kernels
+    if (dbg_knob("MIA_NO_ROWS_FWD")) return false;
     if (mia_ss_num_chunks(L) != 1) return false;                // whole rows, one checkpoint
     auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
     if (!dense(p.u_batch_stride, p.u_d_stride) || !dense(p.delta_batch_stride, p.delta_d_stride) ||
@@ -384,7 +423,7 @@ bool plan_rows_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsBwdArg
     const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
     const int rpg = p.dim / p.n_groups;
     if (p.dstate != 1 || p.z || p.delta_dim != p.dim || (rpg % 32) || (L % 4)) return false;
-    if (getenv("MIA_NO_ROWS_BWD")) return false;                // debugging knob: force the warp-scan kernels
+    if (dbg_knob("MIA_NO_ROWS_BWD")) return false;
     const int CH = mia::kRowsChunk;
     const int nch = (L + CH - 1) / CH;
     // long rows: x must hold a checkpoint every 256 tokens, and the per-row pieces of a tile must be 16-byte aligned
@@ -399,7 +438,7 @@ bool plan_rows_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsBwdArg
     r.batch = p.batch; r.dim = p.dim; r.L = L; r.G = p.n_groups; r.rows_per_group = rpg; r.softplus = p.delta_softplus;
     r.n_chunks = nch;
     const int span = nch == 1 ? L : CH;                         // tokens of a row resident at a time
-    r.t0_pct = getenv("MIA_T0_PCT") ? atoi(getenv("MIA_T0_PCT")) : 52;   // share of a chunk for the half that has no Gs to accumulate
+    r.t0_pct = dbg_int("MIA_T0_PCT", 52);   // share of a chunk for the half that has no Gs to accumulate
     const int T0 = (span * r.t0_pct / 100) / 4 * 4;
     const int longer = T0 > span - T0 ? T0 : span - T0;
     r.nblk = (longer + mia::kBlk - 1) / mia::kBlk;
@@ -429,6 +468,62 @@ bool plan_rows_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsBwdArg
     return true;
 }
 
+// Deterministic d_state 16 backward (scan_bwd_rowsn.cuh): eligibility + argument block.
+bool plan_rowsn_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsNBwdArgs &r, int &grid) {
+    const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
+    const int rpg = p.dim / p.n_groups;
+    RowsNSplit sp;
+    if (!rowsn_bwd_split(p, di.sms, kRowsNCtasPerSm, sp)) return false;
+    if (dbg_knob("MIA_NO_ROWS_BWD")) return false;
+    auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
+    if (!dense(p.u_batch_stride, p.u_d_stride) || !dense(p.delta_batch_stride, p.delta_d_stride) ||
+        !dense(p.dout_batch_stride, p.dout_d_stride) || !dense(p.du_batch_stride, p.du_d_stride) ||
+        !dense(p.ddelta_batch_stride, p.ddelta_d_stride)) return false;
+    if (((uintptr_t)p.u | (uintptr_t)p.delta | (uintptr_t)p.dout) & 15) return false;
+    if (p.z) {
+        if (!dense(p.z_batch_stride, p.z_d_stride) || !dense(p.out_saved_batch_stride, p.out_saved_d_stride) ||
+            !dense(p.dz_batch_stride, p.dz_d_stride)) return false;
+        if (((uintptr_t)p.z | (uintptr_t)p.out_saved) & 15) return false;
+    }
+    memset(&r, 0, sizeof(r));
+    r.batch = p.batch; r.dim = p.dim; r.L = L; r.G = p.n_groups; r.rows_per_group = rpg;
+    r.softplus = p.delta_softplus; r.has_z = p.z != nullptr;
+    r.n_oct = sp.n_oct; r.oct_per_cta = sp.oct_per_cta; r.oct_per_group = sp.oct_per_group; r.max_parts = sp.max_parts;
+    r.nblk = (L + mia::kRnBlk - 1) / mia::kRnBlk;
+    r.Lp = r.nblk * mia::kRnBlk;
+    r.pitch_s = r.Lp + 4;
+    r.pitch_acc = r.Lp + 4;
+    // B / C rows [16 states][pitch]: consecutive state rows 16 bytes apart modulo 128, so that the 8 state pairs of a
+    // quarter warp read 8 different 16-byte bank windows
+    r.pitch_bc = r.Lp;
+    while ((r.pitch_bc * es) % 128 != 16) r.pitch_bc += 16 / es;
+    int off = 0;
+    auto take = [&](int bytes) { int o = off; off += round_up(bytes, 128); return o; };
+    r.off_raw_u = take(mia::kRnOct * L * es);
+    r.off_raw_d = take(mia::kRnOct * L * es);
+    r.off_raw_o = take(mia::kRnOct * L * eo);
+    if (p.z) { r.off_raw_z = take(mia::kRnOct * L * es); r.off_raw_os = take(mia::kRnOct * L * eo); }
+    r.off_sm = take(4 * r.pitch_s * 4);
+    r.off_su = take(4 * r.pitch_s * 4);
+    r.off_sy = take(4 * r.pitch_s * 4);
+    r.off_b = take(16 * r.pitch_bc * es);
+    r.off_c = take(16 * r.pitch_bc * es);
+    r.off_acc = take(2 * 16 * r.pitch_acc * 4);
+    r.off_ck = take(r.nblk * 32 * 8);
+    r.off_ckm = take(r.nblk * 4 * 4);
+    r.off_x = take((4 * mia::kRnWarps * 32 + mia::kRnWarps * 4) * 8);
+    r.off_bar = take(8);
+    r.smem_bytes = off;
+    if (r.smem_bytes > di.smem_optin) return false;
+    r.u = p.u; r.delta = p.delta; r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.dout = p.dout;
+    r.z = p.z; r.out_saved = p.out_saved; r.du = p.du; r.ddelta = p.ddelta; r.dz = p.dz;
+    r.A_ds = p.A_d_stride; r.A_ns = p.A_dstate_stride;
+    r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.B_ns = p.B_dstate_stride;
+    r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride; r.C_ns = p.C_dstate_stride;
+    grid = sp.grid;
+    return true;
+}
+
 template <typename F>
 int dispatch(int itype, F &&f) {
     switch (itype) {
@@ -442,6 +537,7 @@ int dispatch(int itype, F &&f) {
 // Finalize: fold the backward's partials in a fixed order (deterministic) and cast to the output dtypes.
 struct FinArgs {
     int batch, dim, L, N, G, delta_dim, ratio, tiles, bc_atomic, Lp, has_D, has_bias;
+    int oct_per_cta, oct_per_group;          // > 0: partials of scan_bwd_rowsn.cuh, group bg has (c_hi - c_lo + 1) <= tiles of them
     const float *part_dA, *part_dD, *part_dbias, *acc_dB, *acc_dC, *ddelta_full;
     float *dA, *dD, *dbias;
     void *dB, *dC, *ddelta;
@@ -477,8 +573,13 @@ __global__ void ss_finalize_kernel(const __grid_constant__ FinArgs f) {
                 } else {
                     const float *p0 = acc + (((size_t)(b * f.G + g) * f.tiles) * f.N + n) * f.L + l;
                     const size_t step = (size_t)f.N * f.L;
+                    int nt = f.tiles;
+                    if (f.oct_per_cta > 0) {             // partial slots actually written for this group (CTAs it straddles)
+                        const long long o0 = (long long)(b * f.G + g) * f.oct_per_group;
+                        nt = (int)((o0 + f.oct_per_group - 1) / f.oct_per_cta - o0 / f.oct_per_cta) + 1;
+                    }
 #pragma unroll 4
-                    for (int tl = 0; tl < f.tiles; ++tl) sum += p0[tl * step];
+                    for (int tl = 0; tl < nt; ++tl) sum += p0[tl * step];
                 }
                 raw *dst = reinterpret_cast<raw *>(isC ? f.dC : f.dB);
                 const long long o = isC ? (b * f.dC_bs + g * f.dC_gs + n * f.dC_ns + l) : (b * f.dB_bs + g * f.dB_gs + n * f.dB_ns + l);
@@ -619,12 +720,13 @@ int mia_selective_scan_fwd(const mia_ss_params *pp, void *cuda_stream) {
 
 size_t mia_selective_scan_bwd_workspace(const mia_ss_params *pp) {
     if (!pp) return 0;
+    if (validate_sizes(*pp) != MIA_OK) return 0;     // sizes that the backward itself would reject
     DeviceInfo di;
     if (device_info(di) != MIA_OK) { di.sms = 148; di.smem_optin = 232448; }
     Plan pl;
     mia::ScanArgs a;
     if (plan_and_layout(*pp, di, true, pl, a) != MIA_OK) return 0;
-    return workspace_layout(*pp, pl).total;
+    return workspace_layout(*pp, pl, di.sms).total;
 }
 
 int mia_selective_scan_bwd(const mia_ss_params *pp, void *cuda_stream) {
@@ -646,7 +748,7 @@ int mia_selective_scan_bwd(const mia_ss_params *pp, void *cuda_stream) {
     a.osaved_bs = p.out_saved_batch_stride; a.osaved_ds = p.out_saved_d_stride;
     a.du_bs = p.du_batch_stride; a.du_ds = p.du_d_stride; a.dd_bs = p.ddelta_batch_stride; a.dd_ds = p.ddelta_d_stride;
     a.dz_bs = p.dz_batch_stride; a.dz_ds = p.dz_d_stride;
-    const WorkspaceLayout w = workspace_layout(p, pl);
+    const WorkspaceLayout w = workspace_layout(p, pl, di.sms);
     if (!p.workspace || p.workspace_bytes < w.total)
         return fail(MIA_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total, p.workspace ? p.workspace_bytes : (size_t)0);
     MIA_CHECK(((uintptr_t)p.workspace & 255) == 0, "workspace must be 256-byte aligned");
@@ -655,9 +757,12 @@ int mia_selective_scan_bwd(const mia_ss_params *pp, void *cuda_stream) {
     a.acc_dB = (float *)(ws + w.acc_dB); a.acc_dC = (float *)(ws + w.acc_dC);
     a.ddelta_full = (float *)(ws + w.ddelta_full);
     a.bc_atomic = w.bc_atomic;
-    if (w.bc_atomic && getenv("MIA_DEBUG_SKIP_RED")) a.bc_atomic = 2;   // timing experiment only: dB / dC are wrong
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    if (w.bc_atomic) {
+    mia::RowsNBwdArgs rn;
+    int rn_grid = 0;
+    const bool use_rowsn = plan_rowsn_bwd(p, di, rn, rn_grid);
+    if (use_rowsn) a.bc_atomic = 0;
+    if (a.bc_atomic) {
         MIA_CUDA(cudaMemsetAsync(a.acc_dB, 0, w.acc_bytes, stream));
         MIA_CUDA(cudaMemsetAsync(a.acc_dC, 0, w.acc_bytes, stream));
         g_launches.fetch_add(2);
@@ -665,7 +770,15 @@ int mia_selective_scan_bwd(const mia_ss_params *pp, void *cuda_stream) {
     int rc = 0, bc_parts = pl.split;
     mia::RowsBwdArgs rb;
     int rgrid = 0;
-    if (plan_rows_bwd(p, di, rb, rgrid)) {
+    if (use_rowsn) {
+        rn.part_dA = a.part_dA; rn.part_dD = a.part_dD; rn.part_dbias = a.part_dbias; rn.acc_dB = a.acc_dB; rn.acc_dC = a.acc_dC;
+        bc_parts = rn.max_parts;
+        const bool of32 = p.otype == MIA_F32 && p.itype != MIA_F32;
+        rc = dispatch(p.itype, [&](auto *tag) {
+            using T = typename std::remove_pointer<decltype(tag)>::type;
+            return (int)mia::launch_bwd_rowsn<T>(rn, rn_grid, of32, stream);
+        });
+    } else if (plan_rows_bwd(p, di, rb, rgrid)) {
         rb.part_dA = a.part_dA; rb.part_dD = a.part_dD; rb.part_dbias = a.part_dbias; rb.acc_dB = a.acc_dB; rb.acc_dC = a.acc_dC;
         bc_parts = rb.rows_per_group / 32;
         const bool of32 = p.otype == MIA_F32 && p.itype != MIA_F32;
@@ -686,7 +799,8 @@ int mia_selective_scan_bwd(const mia_ss_params *pp, void *cuda_stream) {
     FinArgs f;
     memset(&f, 0, sizeof(f));
     f.batch = p.batch; f.dim = p.dim; f.L = p.seqlen; f.N = p.dstate; f.G = p.n_groups; f.delta_dim = p.delta_dim;
-    f.ratio = p.dim / p.delta_dim; f.tiles = bc_parts; f.bc_atomic = w.bc_atomic; f.Lp = (p.seqlen + 3) & ~3;
+    f.ratio = p.dim / p.delta_dim; f.tiles = bc_parts; f.bc_atomic = a.bc_atomic; f.Lp = (p.seqlen + 3) & ~3;
+    if (use_rowsn) { f.oct_per_cta = rn.oct_per_cta; f.oct_per_group = rn.oct_per_group; }
     f.part_dA = a.part_dA; f.part_dD = a.part_dD; f.part_dbias = a.part_dbias; f.acc_dB = a.acc_dB; f.acc_dC = a.acc_dC;
     f.ddelta_full = a.ddelta_full;
     f.dA = p.dA; f.dD = p.dD; f.dbias = p.ddelta_bias; f.dB = p.dB; f.dC = p.dC; f.ddelta = p.ddelta;

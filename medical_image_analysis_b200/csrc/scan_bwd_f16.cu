@@ -1,7 +1,9 @@
 // bwd selective-scan kernels, f16 activations (one translation unit per dtype so they compile in parallel)
 #include "scan_bwd_fast.cuh"
 #include "scan_bwd_rows.cuh"
+#include "scan_bwd_rowsn.cuh"
 namespace mia {
 template cudaError_t launch_bwd_any<__half>(const ScanArgs &, int, cudaStream_t);
 template cudaError_t launch_bwd_rows<__half>(const RowsBwdArgs &, int, bool, cudaStream_t);
+template cudaError_t launch_bwd_rowsn<__half>(const RowsNBwdArgs &, int, bool, cudaStream_t);
 }  // namespace mia

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1) ss_bwd_fastn_kernel(const __grid_
                             tt = a2[k].y * hm; hm = tt + ah2[k].y; ah2[k].y = tt; hh.y = hm;
                             dCv[k] = mul2(dy2[k], hh);
                         }
-                        if (nval > 0 && a.bc_atomic != 2) {
+                        if (nval > 0) {
                             red_add_v4(pC, dCv[0].x, dCv[0].y, dCv[1].x, dCv[1].y);
                             if (nval > 4) red_add_v4(pC + 4, dCv[2].x, dCv[2].y, dCv[3].x, dCv[3].y);
                         }
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) ss_bwd_fastn_kernel(const __grid_
                             dAm2 = fma2(gah, m2[k], dAm2);                      // dA / ln2
                             B2[k] = mul2(g, mul2v[k]);                          // dB
                         }
-                        if (nval > 0 && a.bc_atomic != 2) {
+                        if (nval > 0) {
                             red_add_v4(pB, B2[0].x, B2[0].y, B2[1].x, B2[1].y);
                             if (nval > 4) red_add_v4(pB + 4, B2[2].x, B2[2].y, B2[3].x, B2[3].y);
                         }

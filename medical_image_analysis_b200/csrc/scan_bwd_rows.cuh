@@ -374,11 +374,6 @@ cudaError_t launch_bwd_rows(const RowsBwdArgs &a, int grid, bool dout_f32, cudaS
     else kernel = dout_f32 ? &ss_bwd_rows_kernel<T, false, true> : &ss_bwd_rows_kernel<T, false, false>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
     if (e != cudaSuccess) return e;
-    if (getenv("MIA_DEBUG")) {
-        int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 64, a.smem_bytes);
-        fprintf(stderr, "[mia] ss_bwd_rows: grid %d, smem %d B, resident CTAs/SM %d\n", grid, a.smem_bytes, nb);
-    }
     kernel<<<grid, 64, a.smem_bytes, stream>>>(a);
     return cudaGetLastError();
 }

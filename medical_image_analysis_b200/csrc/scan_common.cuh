@@ -49,7 +49,7 @@ struct ScanArgs {
     const void *dout, *out_saved;
     void *du, *ddelta, *dz;
     float *part_dA, *part_dD, *part_dbias;   // (batch, dim, N) / (batch, dim) / (batch, dim) f32 partials
-    float *acc_dB, *acc_dC;                  // N <= 2: (n_seg, N, L) partials ; else (batch, G, N, Lp) atomics
+    float *acc_dB, *acc_dC;                  // d_state 1: (parts, N, L) partials ; warp-scan kernels with d_state > 1: (batch, G, N, Lp) red.add accumulators
     float *ddelta_full;                      // (batch, dim, L) f32 when delta_ratio > 1
     int bc_atomic;
     // strides (elements)

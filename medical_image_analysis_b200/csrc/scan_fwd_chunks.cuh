@@ -4,7 +4,7 @@
 // rows there are only 384 such warps for 148 SMs (2.6 per SM) and each is latency-bound for 6400 tokens.  The recurrence
 // h = a h + b is associative, so the row is cut at the 256-token checkpoint boundaries of x and done in three launches:
 //   A  per (32-row batch, chunk): local scan from h = 0, only the aggregate (P = prod a, h_local) is kept -> x[b][d][c];
-//   B  per row: the chunk aggregates are chained serially, x[b][d][c] <- (P_c, state after chunk c)   (nch steps);
+//   B  per row: the chunk aggregates are chained serially, x[b][d][c] <- (prod a so far, state after chunk c)   (nch steps);
 //   C  per (32-row batch, chunk): the real pass, starting from the state after chunk c - 1, writes the outputs.
 // 1.6x the arithmetic of the serial kernel (pass A needs the same 3 MUFU per token), but 25x the parallelism at L = 6400;
 // u and delta are read twice (the kernels are not HBM-bound).  x is exactly what the serial kernels would have written,
@@ -138,17 +138,19 @@ __global__ void __launch_bounds__(32) ss_fwd_chunk_kernel(const __grid_constant_
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-// pass B: chain the chunk aggregates of every row; x[row][c] <- (P_c, state after chunk c)
+// pass B: chain the chunk aggregates of every row; x[row][c] <- (prod a from the row start, state after chunk c): the same
+// running prefix the serial kernels (and the reference, fwd_kernel_oflex.cuh:156-166) leave in x
 template <typename T>   // (template only so that the header can live in several translation units)
 __global__ void __launch_bounds__(256) ss_fwd_chunk_combine_kernel(float2 *x, const int n_rows, const int nch) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n_rows) return;
     float2 *xr = x + (size_t)row * nch;
-    float h = 0.f;
+    float h = 0.f, P = 1.f;
     for (int c = 0; c < nch; ++c) {
         const float2 v = xr[c];
         h = fmaf(v.x, h, v.y);
-        xr[c] = make_float2(v.x, h);
+        P *= v.x;
+        xr[c] = make_float2(P, h);
     }
 }
 

@@ -12,7 +12,7 @@ from __future__ import annotations
 import sys
 import types
 
-from . import selective_scan_cuda, selective_scan_cuda_core, selective_scan_cuda_oflex, selective_scan_interface as ssi
+from . import layernorm, selective_scan_cuda, selective_scan_cuda_core, selective_scan_cuda_oflex, selective_scan_interface as ssi
 
 
 def _module(name, **attrs):
@@ -35,7 +35,11 @@ def install(force: bool = False) -> None:
                     selective_scan_fn=ssi.selective_scan_fn, SelectiveScanFn=ssi.SelectiveScanFn,
                     mamba_inner_fn=ssi.mamba_inner_fn, mamba_inner_fn_no_out_proj=ssi.mamba_inner_fn_no_out_proj,
                     bimamba_inner_fn=ssi.bimamba_inner_fn)
-    ops = _module("mamba_ssm.ops", selective_scan_interface=iface)
+    # models_mamba.py:24 / mamba_simple.py:30: every arm_*_pz16 factory passes rms_norm=True, so RMSNorm must be a class
+    ln = _module("mamba_ssm.ops.triton.layernorm", RMSNorm=layernorm.RMSNorm, layer_norm_fn=layernorm.layer_norm_fn,
+                 rms_norm_fn=layernorm.rms_norm_fn)
+    tri = _module("mamba_ssm.ops.triton", layernorm=ln)     # selective_state_update (only Mamba.step) stays an ImportError
+    ops = _module("mamba_ssm.ops", selective_scan_interface=iface, triton=tri)
     class GenerationMixin:  # imported (unused) by models_mamba.py:20 / models_pretrain.py:20
         pass
 
@@ -46,5 +50,5 @@ def install(force: bool = False) -> None:
     hf = _module("mamba_ssm.utils.hf", load_config_hf=_no_hub, load_state_dict_hf=_no_hub)
     utils = _module("mamba_ssm.utils", generation=gen, hf=hf)
     root = _module("mamba_ssm", ops=ops, utils=utils, __version__="0+b200")
-    cc = _module("causal_conv1d", causal_conv1d_fn=ssi.causal_conv1d_fn, causal_conv1d_update=None)
+    cc = _module("causal_conv1d", causal_conv1d_fn=ssi.causal_conv1d_fn, causal_conv1d_update=ssi.causal_conv1d_update)
     del root, cc

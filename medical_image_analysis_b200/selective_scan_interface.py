@@ -226,6 +226,20 @@ def causal_conv1d_fn(x, weight, bias=None, activation=None):
     return CausalConv1dFn.apply(x, weight, bias, activation is not None)
 
 
+def causal_conv1d_update(x, conv_state, weight, bias=None, activation=None):
+    """causal_conv1d.causal_conv1d_update (single-token decode step; only reached from ``Mamba.step``,
+    mamba_simple.py:732-738, which no train.py of the reference calls): x (batch, dim), conv_state (batch, dim, width)
+    rolled in place, weight (dim, width).  Not a hot path: stated with torch ops."""
+    if activation not in (None, "silu", "swish"):
+        raise NotImplementedError("activation must be None, silu or swish")
+    conv_state.copy_(torch.roll(conv_state, shifts=-1, dims=-1))
+    conv_state[:, :, -1] = x
+    out = torch.sum(conv_state * weight.to(conv_state.dtype), dim=-1)
+    if bias is not None:
+        out = out + bias.to(out.dtype)
+    return (F.silu(out) if activation is not None else out).to(x.dtype)
+
+
 def _inner_projections(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, B, C, B_proj_bias, C_proj_bias, d_state):
     if B is not None or C is not None:
         raise NotImplementedError("only input-dependent B / C (B=None, C=None), as at every call site of the reference")

@@ -31,7 +31,9 @@ def _cs_call(fn, src: torch.Tensor, dst: torch.Tensor, B: int, C: int, H: int, W
         raise RuntimeError("CrossScan / CrossMerge support float32, float16 and bfloat16")
     with torch.cuda.device(src.device):
         stream = ctypes.c_void_p(torch.cuda.current_stream(src.device).cuda_stream)
-        _lib.check(fn(src.data_ptr(), dst.data_ptr(), B, C, H, W, _DT[src.dtype], stream), "cross scan/merge")
+        rc = fn(src.data_ptr(), dst.data_ptr(), B, C, H, W, _DT[src.dtype], stream)
+        if rc != 0:
+            raise RuntimeError(f"cross scan/merge: {_lib.lib().mia_cs_last_error().decode()} (code {rc})")
 
 
 class DWConv2dFn(torch.autograd.Function):
