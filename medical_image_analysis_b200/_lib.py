@@ -77,6 +77,9 @@ def lib() -> ctypes.CDLL:
         L.mia_dwconv2d_bwd.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ci, ci, ci, ci, ci, ci, _vp]
         L.mia_dwconv2d_bwd.restype = ci
         L.mia_dwconv2d_last_error.restype = ctypes.c_char_p
+        L.mia_gemm_tn.argtypes = [_vp, _vp, _vp, _vp, ci, ci, ci, ll, ll, ll, ci, ci, ci, _vp]
+        L.mia_gemm_tn.restype = ci
+        L.mia_gemm_last_error.restype = ctypes.c_char_p
         if L.mia_abi_version() != 1:
             raise RuntimeError(f"libmia_scan.so ABI version {L.mia_abi_version()} != 1: rebuild it")
         _lib = L

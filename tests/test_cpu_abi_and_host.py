@@ -21,10 +21,16 @@ def _lib():
 
 
 def test_library_exports_every_declared_symbol():
+    """Every function any include/*.h declares is exported by libmia_scan.so."""
+    import glob
     lib = _lib()
-    text = open(HEADER).read()
-    body = text[text.index('extern "C"'):]
-    names = sorted(set(re.findall(r"\b(mia_[a-z_0-9]+)\s*\(", body)))
+    names = set()
+    for hdr in sorted(glob.glob(os.path.join(ROOT, "include", "*.h"))):
+        text = open(hdr).read()
+        body = text[text.index('extern "C"'):]
+        names |= set(re.findall(r"\b(mia_[a-z_0-9]+)\s*\(", body))
+    names = sorted(names)
+    assert {"mia_gemm_tn", "mia_gemm_last_error", "mia_cs_last_error"} <= set(names)
     assert {"mia_selective_scan_fwd", "mia_selective_scan_bwd", "mia_selective_scan_bwd_workspace", "mia_last_error",
             "mia_abi_version", "mia_ss_num_chunks", "mia_ss_chunk_len", "mia_launch_count"} <= set(names)
     for n in names:
@@ -72,6 +78,19 @@ def test_c_abi_validation_without_gpu():
     p.dstate, p.itype = 4, 7
     assert lib.mia_selective_scan_bwd(ctypes.byref(p), None) == -1
     assert b"float32, float16 or bfloat16" in lib.mia_last_error()
+
+
+def test_gemm_validation_without_gpu():
+    lib = _lib()
+    buf = ctypes.create_string_buffer(64)
+    ptr = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.mia_gemm_tn(None, None, None, None, 4, 4, 8, 8, 8, 4, 2, 2, 0, None) == -1
+    assert lib.mia_gemm_tn(ptr, ptr, None, ptr, 4, 4, 8, 8, 8, 4, 0, 0, 0, None) == -1           # fp32 inputs
+    assert b"bf16 or fp16" in lib.mia_gemm_last_error()
+    assert lib.mia_gemm_tn(ptr, ptr, None, ptr, 4, 4, 12, 12, 12, 4, 2, 2, 0, None) == -1        # pitch not a multiple of 8
+    assert b"multiples of 8" in lib.mia_gemm_last_error()
+    assert lib.mia_gemm_tn(ptr, ptr, None, ptr, 4, 4, 8, 8, 8, 4, 2, 2, 9, None) == -1
+    assert b"activation" in lib.mia_gemm_last_error()
 
 
 def test_host_checks_raise_runtime_error():
