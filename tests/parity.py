@@ -68,8 +68,18 @@ def cmp_f32(got: torch.Tensor, ref: torch.Tensor, what: str, rtol: float = 1e-5,
     _report(what, err, tol, ref64)
 
 
-def cmp_auto(got: torch.Tensor, ref: torch.Tensor, what: str, n_ulp: float = 1.0):
-    """fp32 tensors by ``cmp_f32``, bf16 / fp16 tensors by ``cmp_stored`` (``n_ulp`` units in the last place)."""
+def long_row_scale(L: int) -> float:
+    """fp32 criterion for rows longer than one 256-token chunk.  h_t is a product of up to L factors a_s = exp(dl_s A): a
+    relative error eps per factor (fp32 rounding, ~1e-7) grows to ~n eps over the n <= L tokens a slowly decaying row
+    remembers, in ANY fp32 evaluation.  Measured here with the reference's own fp32 path (oracle/selective_scan_ref.py, exact
+    libm exp) against the fp64 oracle, reference generators, 256 rows: worst err / (1e-5 |ref| + 2e-5 RMS) = 0.16 at
+    L = 196, 0.52 at L = 2048, 2.24 at L = 6400.  The tolerance therefore scales with the number of chunks."""
+    return max(1.0, L / 256.0)
+
+
+def cmp_auto(got: torch.Tensor, ref: torch.Tensor, what: str, n_ulp: float = 1.0, f32_scale: float = 1.0):
+    """fp32 tensors by ``cmp_f32`` (tolerances times ``f32_scale``, see long_row_scale), bf16 / fp16 tensors by
+    ``cmp_stored`` (``n_ulp`` units in the last place)."""
     if got.dtype == torch.float32:
-        return cmp_f32(got, ref, what)
+        return cmp_f32(got, ref, what, rtol=1e-5 * f32_scale, atol_rms=2e-5 * f32_scale)
     return cmp_stored(got, ref, got.dtype, what, n_ulp=n_ulp)
