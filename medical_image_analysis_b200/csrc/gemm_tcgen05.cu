@@ -14,8 +14,10 @@
 //   warp 1   allocates TMEM (2 accumulator stages of BN fp32 columns) and issues tcgen05.mma.cta_group::1.kind::f16
 //            (SASS UTCHMMA), M = 128, N = BN, K = 16 per instruction, four per 64-wide K block; tcgen05.commit releases the
 //            shared-memory stage and, after the last K block, hands the accumulator stage to the epilogue;
-//   warps 2-5  epilogue: tcgen05.ld (SASS LDTM) 32 lanes x 32 columns at a time, + bias, activation, conversion, 16-byte
-//            global stores; the next tile's MMAs run meanwhile in the other accumulator stage.
+//   warps 2-5  epilogue: tcgen05.ld (SASS LDTM) 32 lanes x 32 columns at a time, + bias, activation, conversion, then
+//            128-byte row chunks into a swizzled shared slab and out through a TMA tensor-map store (SASS UTMASTG:
+//            coalesced full-line writes; per-thread 16-byte global stores only when C's rows are not 16-byte aligned);
+//            the next tile's MMAs run meanwhile in the other accumulator stage.
 // Out-of-range rows / columns / K tail are zero-filled by TMA and masked in the epilogue, so any M, N and any K with
 // K % 8 == 0 (16-byte rows) work.  No split-K: K is at most 16384 (patch-embed conv4/4) and M is large on this path.
 #include <cuda.h>
@@ -51,12 +53,18 @@ struct GemmArgs {
     void *C;
     long long ldc;
     int num_m_blocks, num_n_blocks, num_k_blocks;
+    int tma_store;      // C is written through a tensor map (16-byte aligned rows); else direct 16-byte stores per thread
 };
 
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
                      mia::smem_u32(smem_dst)),
                  "l"(tm), "r"(mia::smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, const void *smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(mia::smem_u32(smem_src)), "r"(c0),
+                 "r"(c1)
                  : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -101,15 +109,18 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     }
 }
 
+constexpr int kEpiSlab = 32 * 128;       // one epilogue staging slab: 32 rows x 128 bytes (one swizzle-128B TMA store box)
+
 template <int BN, int kStages>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                                  const GemmArgs g) {
+                                                                  const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
     extern __shared__ char smem_raw[];
     // SWIZZLE_128B tiles must sit on 1024-byte boundaries
     char *smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int kABytes = kBM * kBK * 2, kBBytes = BN * kBK * 2, kStageBytes = kABytes + kBBytes;
     char *tiles = smem;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
+    char *epi = smem + kStages * kStageBytes;                 // 4 warps x 2 slabs, 1024-byte aligned (swizzle-128B boxes)
+    uint64_t *full = reinterpret_cast<uint64_t *>(epi + 8 * kEpiSlab);
     uint64_t *empty = full + kStages;
     uint64_t *tfull = empty + kStages;        // accumulator stage ready for the epilogue
     uint64_t *tempty = tfull + 2;             // accumulator stage drained
@@ -182,7 +193,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
     } else {
         // ===== epilogue warps 2..5: TMEM lanes of quadrant (warp % 4)
         const int q = warp & 3;
-        int as = 0;
+        int as = 0, chunk = 0;
         uint32_t aph = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int mb = tile % g.num_m_blocks, nb = tile / g.num_m_blocks;
@@ -190,6 +201,56 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
             tc_fence_after();
             const int row = mb * kBM + q * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+            if (g.tma_store) {
+                // 128-byte chunks of the 32-row slab of this warp: registers -> swizzled shared slab -> one TMA store each.
+                // Chunk j of row r sits at r * 128 + ((j ^ (r & 7)) << 4): conflict-free 16-byte stores, and exactly the
+                // SWIZZLE_128B pattern the C tensor map un-does on the way out (coalesced full-line writes).
+                const int cc = g.out_f32 ? 32 : 64;                        // columns per chunk
+                char *slab0 = epi + (warp - 2) * 2 * kEpiSlab;
+                for (int c = 0; c < BN / cc; ++c, ++chunk) {
+                    const int col0 = nb * BN + c * cc;
+                    if (col0 >= g.N) break;                                 // warp-uniform
+                    char *slab = slab0 + (chunk & 1) * kEpiSlab;
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that used this slab 2 chunks ago
+                    __syncwarp();
+                    char *rowp = slab + lane * 128;
+#pragma unroll 1
+                    for (int hlf = 0; hlf < (g.out_f32 ? 1 : 2); ++hlf) {
+                        uint32_t r[32];
+                        tc_ld32(taddr + (uint32_t)(c * cc + hlf * 32), r);
+                        tc_wait_ld();
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            v[j] = __uint_as_float(r[j]);
+                            const int col = col0 + hlf * 32 + j;
+                            if (g.has_bias) v[j] += (col < g.N) ? __ldg(g.bias + col) : 0.f;
+                            v[j] = act_apply(v[j], g.act);
+                        }
+                        if (g.out_f32) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                *reinterpret_cast<float4 *>(rowp + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
+                            uint32_t w[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                if (g.in_f16) { __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]); w[j] = *reinterpret_cast<uint32_t *>(&h); }
+                                else { __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]); w[j] = *reinterpret_cast<uint32_t *>(&h); }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<uint4 *>(rowp + (((hlf * 4 + j) ^ (lane & 7)) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+                        }
+                    }
+                    mia::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmC, slab, col0, mb * kBM + q * 32);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t r[32];
@@ -230,11 +291,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
                     }
                 }
             }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mia::mbar_arrive(tempty + as);
             if (++as == 2) { as = 0; aph ^= 1; }
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // the slabs must outlive their stores
     }
     tc_fence_before();
     __syncthreads();
@@ -262,24 +325,27 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2-D map of a row-major [rows][cols] matrix of 2-byte elements with row pitch ld (elements); box = [box_rows][64 cols], 128B swizzle
-int make_map(CUtensorMap *tm, const void *ptr, long long rows, long long cols, long long ld, int box_rows, int f16) {
+// 2-D map of a row-major [rows][cols] matrix with row pitch ld (elements); box = [box_rows][128 bytes of columns], 128B swizzle.
+// dt: MIA_GEMM_F32 / F16 / BF16
+int make_map(CUtensorMap *tm, const void *ptr, long long rows, long long cols, long long ld, int box_rows, int dt) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return gfail(MIA_GEMM_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const int es = dt == MIA_GEMM_F32 ? 4 : 2;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    const CUresult r = fn(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides,
-                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUtensorMapDataType cdt = dt == MIA_GEMM_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                                        : (dt == MIA_GEMM_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+    const CUresult r = fn(tm, cdt, 2, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return gfail(MIA_GEMM_ECUDA, "cuTensorMapEncodeTiled failed (CUresult %d): rows %lld cols %lld ld %lld", (int)r, rows, cols, ld);
     return MIA_GEMM_OK;
 }
 
 template <int BN, int kStages>
-int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, GemmArgs &g, int sms, cudaStream_t stream) {
-    constexpr int smem = kStages * (kBM * kBK * 2 + BN * kBK * 2) + (2 * kStages + 4) * 8 + 16 + 1024;
+int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, GemmArgs &g, int sms, cudaStream_t stream) {
+    constexpr int smem = kStages * (kBM * kBK * 2 + BN * kBK * 2) + 8 * kEpiSlab + (2 * kStages + 4) * 8 + 16 + 1024;
     auto k = &gemm_tn_kernel<BN, kStages>;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
         return gfail(MIA_GEMM_ECUDA, "cudaFuncSetAttribute(gemm, %d B): %s", smem, cudaGetErrorString(cudaGetLastError()));
@@ -288,7 +354,7 @@ int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, GemmArgs &g, int
     g.num_k_blocks = (g.K + kBK - 1) / kBK;
     const int tiles = g.num_m_blocks * g.num_n_blocks;
     const int grid = tiles < sms ? tiles : sms;
-    k<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, g);
+    k<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, tmC, g);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return gfail(MIA_GEMM_ECUDA, "gemm launch: %s", cudaGetErrorString(e));
     return MIA_GEMM_OK;
@@ -318,14 +384,21 @@ int mia_gemm_tn(const void *A, const void *W, const float *bias, void *C, int M,
     g.M = M; g.N = N; g.K = K; g.act = act; g.out_f32 = out_dtype == MIA_GEMM_F32; g.has_bias = bias != nullptr; g.bias = bias;
     g.in_f16 = in_dtype == MIA_GEMM_F16; g.C = C; g.ldc = ldc;
     const int BN = N <= 64 ? 64 : (N <= 128 || (long long)((M + 127) / 128) * ((N + 255) / 256) < sms ? 128 : 256);
-    CUtensorMap tmA, tmB;
-    if (int rc = make_map(&tmA, A, M, K, lda, kBM, g.in_f16)) return rc;
-    if (int rc = make_map(&tmB, W, N, K, ldw, BN, g.in_f16)) return rc;
+    CUtensorMap tmA, tmB, tmC;
+    if (int rc = make_map(&tmA, A, M, K, lda, kBM, in_dtype)) return rc;
+    if (int rc = make_map(&tmB, W, N, K, ldw, BN, in_dtype)) return rc;
+    const int eo = g.out_f32 ? 4 : 2;
+    g.tma_store = (((uintptr_t)C & 15) == 0) && ((ldc * eo) % 16 == 0);
+    if (g.tma_store) {
+        if (int rc = make_map(&tmC, C, M, N, ldc, 32, out_dtype)) return rc;
+    } else {
+        tmC = tmA;                                   // unused by the kernel on the direct-store path
+    }
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     switch (BN) {
-        case 64: return launch_gemm<64, 8>(tmA, tmB, g, sms, stream);
-        case 128: return launch_gemm<128, 6>(tmA, tmB, g, sms, stream);
-        default: return launch_gemm<256, 4>(tmA, tmB, g, sms, stream);
+        case 64: return launch_gemm<64, 8>(tmA, tmB, tmC, g, sms, stream);
+        case 128: return launch_gemm<128, 6>(tmA, tmB, tmC, g, sms, stream);
+        default: return launch_gemm<256, 4>(tmA, tmB, tmC, g, sms, stream);
     }
 }
 

@@ -113,3 +113,25 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = No
     lead = x.shape[:-1]
     y = LinearTC.apply(x.reshape(-1, x.shape[-1]), weight, bias, act, out_dtype)
     return y.view(*lead, weight.shape[0])
+
+
+def conv2d_patch(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, stride, act: int = ACT_NONE) -> torch.Tensor:
+    """``nn.Conv2d`` with kernel_size == stride and no padding (patch embeddings: models_mamba.py:45, patch_embed.py:25-29) as
+    ONE GEMM over the non-overlapping patches: (B hp wp, C kh kw) x (O, C kh kw)^T on the tcgen05 kernel for bf16 / fp16
+    activations; anything else (fp32, overlapping windows) is the library convolution.  Returns (B, O, hp, wp)."""
+    kh, kw = weight.shape[2:]
+    sh, sw = (stride, stride) if isinstance(stride, int) else tuple(stride)
+    if torch.is_autocast_enabled() and x.is_cuda:
+        x = x.to(torch.get_autocast_dtype("cuda"))
+    if (kh, kw) != (sh, sw) or not x.is_cuda or x.dtype not in (torch.bfloat16, torch.float16):
+        y = F.conv2d(x, weight.to(x.dtype), None if bias is None else bias.to(x.dtype), stride=(sh, sw))
+        return {ACT_NONE: lambda t: t, ACT_RELU: F.relu, ACT_GELU: F.gelu, ACT_SILU: F.silu}[act](y)
+    B, C, H, W = x.shape
+    hp, wp = H // kh, W // kw
+    O = weight.shape[0]
+    if kh == 1 and kw == 1:
+        patches = x.permute(0, 2, 3, 1).reshape(B * hp * wp, C)
+    else:
+        patches = x[:, :, :hp * kh, :wp * kw].reshape(B, C, hp, kh, wp, kw).permute(0, 2, 4, 1, 3, 5).reshape(B * hp * wp, C * kh * kw)
+    y = LinearTC.apply(patches, weight.reshape(O, -1), bias, act, None)
+    return y.view(B, hp, wp, O).permute(0, 3, 1, 2)

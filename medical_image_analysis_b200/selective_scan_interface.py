@@ -247,7 +247,8 @@ def _inner_projections(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj
     x, z = xz.chunk(2, dim=1)
     cw = conv1d_weight.squeeze(1) if conv1d_weight.dim() == 3 else conv1d_weight
     x = causal_conv1d_fn(x, cw, conv1d_bias, "silu")
-    x_dbl = F.linear(x.transpose(1, 2).reshape(-1, x.shape[1]), x_proj_weight)          # (b l, R + 2N)
+    from . import gemm as _gemm
+    x_dbl = _gemm.linear(x.transpose(1, 2).reshape(-1, x.shape[1]), x_proj_weight)     # (b l, R + 2N): tcgen05 GEMM for bf16 / fp16
     R = delta_proj_weight.shape[1]
     N = (x_dbl.shape[1] - R) // 2 if d_state is None else d_state
     delta = (delta_proj_weight @ x_dbl[:, :R].t()).view(delta_proj_weight.shape[0], -1, L).transpose(0, 1)   # (b, d, l)
@@ -275,7 +276,8 @@ def mamba_inner_fn(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_wei
     """mamba_simple.py:650-663: the block above followed by out_proj; returns (b, l, d_model)."""
     y = mamba_inner_fn_no_out_proj(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D,
                                    delta_bias, B_proj_bias, C_proj_bias, delta_softplus)
-    return F.linear(y.transpose(1, 2), out_proj_weight, out_proj_bias)
+    from . import gemm as _gemm
+    return _gemm.linear(y.transpose(1, 2), out_proj_weight, out_proj_bias)
 
 
 def bimamba_inner_fn(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias, A, A_b,

@@ -76,7 +76,8 @@ def test_linear_autograd_matches_torch(act):
     yr = torch.nn.functional.linear(xr, wr, br)
     yr = {0: lambda t: t, 1: torch.relu, 2: torch.nn.functional.gelu}[act](yr)
     yr.backward(dy.double())
-    cmp_stored(y, yr, torch.bfloat16, f"linear act{act} y")
+    # training-mode GELU keeps the bf16 pre-activation for the backward and applies GELU to it: two roundings
+    cmp_stored(y, yr, torch.bfloat16, f"linear act{act} y", n_ulp=2.0 if act == 2 else 1.0)
     cmp_stored(xg.grad, xr.grad, torch.bfloat16, f"linear act{act} dx", n_ulp=2.0)      # dy rounded again after the activation derivative
     cmp_stored(wg.grad, wr.grad, torch.bfloat16, f"linear act{act} dw", n_ulp=2.0)
     assert torch.allclose(bg.grad.double().cpu(), br.grad, rtol=2e-2, atol=2e-2)

@@ -1,0 +1,277 @@
+"""Module-level parity against vectors produced by executing the REFERENCE'S OWN modules (tests/golden/modules_*.npz,
+generator tests/golden/make_golden_modules.py): cross_selective_scan, every SS2D forward family, VSSBlock, VSSM,
+Backbone_VSSM -- same constructor arguments, the reference's state_dict loaded into this repository's classes, same inputs,
+fp32.  What differs from the reference run is only the scan / cross-scan / conv kernels (CUDA here, torch there); the
+reference rounds the merged scan output to bf16 (vmamba.py:420) and so does this path, hence the tolerances: outputs and
+gradients within 2 % of the tensor's RMS + 1 % relative (a bf16 rounding boundary crossed by one of the d_inner inputs of
+the LayerNorm moves an output by ~0.4 % / sqrt(d_inner) of its scale; tensors that never pass that cast are far tighter,
+see the fp32-only cases)."""
+import ast
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+GOLDDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLDDIR, name))
+    cases = {}
+    for key in z.files:
+        tag, name = key.split("|", 1)
+        cases.setdefault(tag, {})[name] = z[key]
+    return cases
+
+
+CASES = _load("modules_vmamba.npz")
+ARM_CASES = _load("modules_arm.npz")
+
+
+def _cfg(case):
+    return eval(str(case["cfg"]), {"nn": nn})      # repr of a plain dict of ints / floats / strings / lists
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _close(got, ref, what, rtol=1e-2, atol_rms=2e-2):
+    got, ref = got.detach().float().cpu().double(), _t(ref).double()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    rms = float(ref.pow(2).mean().sqrt())
+    err = (got - ref).abs()
+    tol = rtol * ref.abs() + atol_rms * max(rms, 1e-12)
+    assert bool((err <= tol).all()), f"{what}: max err {float(err.max()):.3e} (RMS ref {rms:.3e}), {int((err > tol).sum())}/{err.numel()} out"
+
+
+def _load_state(m, case):
+    sd = {k[len("param."):]: _t(v) for k, v in case.items() if k.startswith("param.")}
+    sd.update({k[len("buffer."):]: _t(v) for k, v in case.items() if k.startswith("buffer.")})
+    missing, unexpected = m.load_state_dict(sd, strict=True), None
+    return m
+
+
+def _run(m, case, extra=()):
+    m = m.cuda()
+    x = _t(case["x"]).cuda().requires_grad_()
+    out = m(x, *extra)
+    outs = out if isinstance(out, (tuple, list)) else (out,)
+    loss = sum((o.float() * _t(case[f"w{i}"]).cuda()).sum() for i, o in enumerate(outs))
+    loss.backward()
+    return x, outs
+
+
+def _check(m, case, tag, extra=()):
+    x, outs = _run(m, case, extra)
+    for i, o in enumerate(outs):
+        _close(o, case[f"out{i}"], f"{tag} out{i}")
+    _close(x.grad, case["dx"], f"{tag} dx")
+    for n, p in m.named_parameters():
+        key = f"grad.{n}"
+        if key in case:
+            assert p.grad is not None, f"{tag}: no gradient for {n}"
+            _close(p.grad, case[key], f"{tag} grad {n}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", sorted(t for t in CASES if t.startswith("css")))
+def test_cross_selective_scan_matches_reference(tag):
+    from medical_image_analysis_b200.vmamba import cross_selective_scan
+    from medical_image_analysis_b200.selective_scan_interface import SelectiveScanOflex
+    c = CASES[tag]
+    cfg = _cfg(c)
+    leaf = lambda k: _t(c[k]).cuda().requires_grad_()
+    x, xw, dtw, dtb, A_logs, Ds = (leaf(k) for k in ("x", "xw", "dtw", "dtb", "A_logs", "Ds"))
+    norm = nn.LayerNorm(x.shape[1]).cuda()
+    with torch.no_grad():
+        norm.weight.copy_(_t(c["nw"])); norm.bias.copy_(_t(c["nb"]))
+    out = cross_selective_scan(x, xw, None, dtw, dtb, A_logs, Ds, out_norm=norm, SelectiveScan=SelectiveScanOflex,
+                               no_einsum=(cfg["mode"] == "no_einsum"))
+    (out.float() * _t(c["w"]).cuda()).sum().backward()
+    _close(out, c["out"], tag + " out")
+    for got, key in ((x.grad, "dx"), (xw.grad, "dxw"), (dtw.grad, "ddtw"), (dtb.grad, "ddtb"), (A_logs.grad, "dA_logs"), (Ds.grad, "dDs"),
+                     (norm.weight.grad, "dnw"), (norm.bias.grad, "dnb")):
+        _close(got, c[key], f"{tag} {key}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", sorted((t for t in CASES if t.startswith("ss2d")), key=lambda t: int(t[4:])))
+def test_ss2d_matches_reference_module(tag):
+    from medical_image_analysis_b200.vmamba import SS2D
+    c = CASES[tag]
+    m = _load_state(SS2D(**_cfg(c)), c)
+    _check(m, c, f"{tag} {_cfg(c)['forward_type']}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["vssblock0", "vssblock1"])
+def test_vssblock_matches_reference_module(tag):
+    from medical_image_analysis_b200.vmamba import VSSBlock
+    c = CASES[tag]
+    _check(_load_state(VSSBlock(**_cfg(c)), c), c, tag)
+
+
+@pytest.mark.gpu
+def test_vssm_matches_reference_module():
+    from medical_image_analysis_b200.vmamba import VSSM
+    c = CASES["vssm0"]
+    _check(_load_state(VSSM(**_cfg(c)), c), c, "vssm0")
+    c = CASES["vssm0g"]
+    _check(_load_state(VSSM(**_cfg(c)), c), c, "vssm0 global_features", extra=(True,))
+
+
+@pytest.mark.gpu
+def test_backbone_vssm_matches_reference_module():
+    from medical_image_analysis_b200.vmamba import Backbone_VSSM
+    c = CASES["backbone0"]
+    cfg = {k: v for k, v in _cfg(c).items() if k != "norm_layer"}
+    _check(_load_state(Backbone_VSSM(out_indices=(0, 1), **cfg), c), c, "backbone0")
+
+
+def test_state_dict_keys_match_reference_modules():
+    """CPU: constructing every golden configuration yields exactly the reference's parameter / buffer names and shapes."""
+    from medical_image_analysis_b200.vmamba import SS2D, VSSM, Backbone_VSSM, VSSBlock
+    for tag, c in CASES.items():
+        if tag.startswith("css"):
+            continue
+        cfg = _cfg(c)
+        if tag.startswith("ss2d"):
+            m = SS2D(**cfg)
+        elif tag.startswith("vssblock"):
+            m = VSSBlock(**cfg)
+        elif tag.startswith("vssm"):
+            m = VSSM(**cfg)
+        else:
+            m = Backbone_VSSM(out_indices=(0, 1), **{k: v for k, v in cfg.items() if k != "norm_layer"})
+        want = {k.split(".", 1)[1]: tuple(v.shape) for k, v in c.items() if k.startswith("param.") or k.startswith("buffer.")}
+        have = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert want == have, (tag, set(want) ^ set(have))
+
+
+def test_unbuildable_reference_configurations_fail_the_same_way():
+    from medical_image_analysis_b200.vmamba import SS2D
+    with pytest.raises(AttributeError):
+        SS2D(d_model=8, d_state=2, dt_rank=3, forward_type="xv2a")      # vmamba.py:888: del before create
+    with pytest.raises(AssertionError):
+        SS2D(d_model=8, forward_type="v0", channel_first=True)          # vmamba.py:606-607
+
+
+# ---- ARM / Vim side (tests/golden/modules_arm.npz): the reference's Mamba mixer and ARM encoder, its fused ops evaluated by its own
+# slow path.  No bf16 cast on this path: fp32 end to end -> tight tolerances.
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", sorted(t for t in ARM_CASES if t.startswith("mamba")))
+def test_mamba_mixer_matches_reference_module(tag):
+    from medical_image_analysis_b200.arm import Mamba
+    c = ARM_CASES[tag]
+    m = _load_state(Mamba(**_cfg(c)), c).cuda()
+    x = _t(c["x"]).cuda().requires_grad_()
+    out = m(x)
+    (out.float() * _t(c["w0"]).cuda()).sum().backward()
+    kw = dict(rtol=2e-4, atol_rms=2e-4)
+    _close(out, c["out0"], tag + " out", **kw)
+    _close(x.grad, c["dx"], tag + " dx", **kw)
+    for n, p in m.named_parameters():
+        if f"grad.{n}" in c:
+            _close(p.grad, c[f"grad.{n}"], f"{tag} grad {n}", **kw)
+
+
+@pytest.mark.gpu
+def test_arm_encoder_matches_reference_module():
+    from medical_image_analysis_b200.arm import ARM
+    c = ARM_CASES["arm0"]
+    m = _load_state(ARM(**_cfg(c)), c).cuda()
+    x = _t(c["x"]).cuda().requires_grad_()
+    out = m(x)
+    (out.float() * _t(c["w0"]).cuda()).sum().backward()
+    kw = dict(rtol=5e-4, atol_rms=5e-4)
+    _close(out, c["out0"], "arm0 out", **kw)
+    _close(x.grad, c["dx"], "arm0 dx", **kw)
+    for n, p in m.named_parameters():
+        if f"grad.{n}" in c:
+            _close(p.grad, c[f"grad.{n}"], f"arm0 grad {n}", **kw)
+
+
+def test_arm_state_dict_keys_match_reference():
+    from medical_image_analysis_b200.arm import ARM, Mamba
+    for tag, c in ARM_CASES.items():
+        m = (Mamba if tag.startswith("mamba") else ARM)(**_cfg(c))
+        want = {k.split(".", 1)[1]: tuple(v.shape) for k, v in c.items() if k.startswith("param.") or k.startswith("buffer.")}
+        have = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert want == have, (tag, set(want) ^ set(have))
+
+
+def test_arm_factories_build_through_dropin():
+    """every registered ARM factory passes rms_norm=True -> RMSNorm must be a class (dropin registers it)."""
+    import sys
+    import medical_image_analysis_b200.dropin as dropin
+    dropin.install(force=True)
+    from mamba_ssm.ops.triton.layernorm import RMSNorm, layer_norm_fn, rms_norm_fn
+    assert isinstance(RMSNorm, type) and callable(layer_norm_fn) and callable(rms_norm_fn)
+    from medical_image_analysis_b200.arm import arm_base_pz16
+    net = arm_base_pz16(img_size=32, drop_path_rate=0.0)      # 2 x 2 patches + cls: cheap to construct on CPU
+    assert len(net.layers) == 12 and net.layers[0].mixer.bimamba_type == "v3" and net.layers[0].mixer.d_inner == 768
+    y = torch.randn(2, 5, 768)
+    assert torch.allclose(RMSNorm(768)(y), y * torch.rsqrt(y.pow(2).mean(-1, keepdim=True) + 1e-5), atol=1e-5)
+
+
+# ---- MAE side (tests/golden/modules_mae.npz): the reference's SmallPatchEmbed and MaskedAutoencoderViT (timm's Block restated in
+# the generator: the vectors pin the reference's patch encode, masking, gather / scatter and decoder orchestration).
+MAE_CASES = _load("modules_mae.npz")
+
+
+@pytest.mark.gpu
+def test_small_patch_embed_matches_reference_module():
+    from medical_image_analysis_b200.mae import SmallPatchEmbed
+    c = MAE_CASES["spe0"]
+    m = _load_state(SmallPatchEmbed(**_cfg(c)), c).cuda()
+    x = _t(c["x"]).cuda().requires_grad_()
+    out = m(x)
+    (out.float() * _t(c["w0"]).cuda()).sum().backward()
+    kw = dict(rtol=2e-4, atol_rms=2e-4)
+    _close(out, c["out0"], "spe0 out", **kw)
+    _close(x.grad, c["dx"], "spe0 dx", **kw)
+    for n, p in m.named_parameters():
+        _close(p.grad, c[f"grad.{n}"], f"spe0 grad {n}", **kw)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mask_type", [0, 1])
+def test_mae_model_matches_reference_module(mask_type):
+    from medical_image_analysis_b200.mae import MaskedAutoencoderViT
+    c = MAE_CASES[f"mae{mask_type}"]
+    m = MaskedAutoencoderViT(**_cfg(c))
+    sd = {k[len("param."):]: _t(v) for k, v in c.items() if k.startswith("param.")}
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    img = torch.randn(1, 1, 1280, 1280, generator=torch.Generator().manual_seed(int(c["img_seed"][0])))
+    assert abs(float(img.double().sum()) - float(c["img_checksum"][0])) < 1e-6 * 1280 * 1280, "torch RNG drifted: regenerate golden"
+    noise = _t(c["noise0"]).cuda() if mask_type == 0 else (_t(c["noise0"]).cuda(), _t(c["noise1"]).cuda())
+    loss, mask = m(img.cuda(), mask_type, 0.85, 0.95, noise=noise)
+    assert torch.equal(mask.cpu(), _t(c["mask"])), "masking differs from the reference"
+    (loss * _t(c["w"]).cuda()).sum().backward()
+    kw = dict(rtol=5e-4, atol_rms=5e-4)
+    _close(loss, c["loss"], f"mae{mask_type} loss", **kw)
+    for n, p in m.named_parameters():
+        if f"grad.{n}" in c:
+            _close(p.grad, c[f"grad.{n}"], f"mae{mask_type} grad {n}", **kw)
+
+
+def test_mae_state_dict_and_masking_on_cpu():
+    """CPU: names / shapes of the reference model; masking reproduces the reference's mask from its recorded draws."""
+    from medical_image_analysis_b200.mae import MaskedAutoencoderViT, SmallPatchEmbed, get_2d_sincos_pos_embed
+    c = MAE_CASES["mae1"]
+    m = MaskedAutoencoderViT(**_cfg(c))
+    want = {k[len("param."):]: tuple(v.shape) for k, v in c.items() if k.startswith("param.")}
+    assert want == {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert np.allclose(m.pos_embed[0].numpy(), get_2d_sincos_pos_embed(16, 20, cls_token=True), atol=1e-6)
+    x = torch.zeros(1, 400, 4)
+    _, mask, ids = m.random_masking_yiliao(x, 0.85, 0.95, _t(c["noise0"]), _t(c["noise1"]))
+    assert torch.equal(mask, _t(c["mask"]))
+    _, mask0, _ = m.random_masking(x, 0.85, _t(MAE_CASES["mae0"]["noise0"]))
+    assert torch.equal(mask0, _t(MAE_CASES["mae0"]["mask"]))
+    sp = SmallPatchEmbed(**_cfg(MAE_CASES["spe0"]))
+    assert {k: tuple(v.shape) for k, v in sp.state_dict().items()} == \
+        {k[len("param."):]: tuple(v.shape) for k, v in MAE_CASES["spe0"].items() if k.startswith("param.")}
