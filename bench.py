@@ -3,12 +3,15 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME] [--no-extras]
 
-A step = one forward + one backward of the selective-scan op over one synthetic batch with SS2D's shapes
-(d_inner 768 -> R = 4*768 = 3072 scan rows, G = 4 B/C groups).  One patch-token = one (image, position) over
-all R rows.  `value` is measured with inputs resident in HBM; `e2e` goes through the same C-ABI calls but
-starts from pinned HOST buffers and ends with the results back in host memory (copies inside the timed region).
-N > 1 (torchrun): pure data parallelism, per-GPU batch fixed (weak scaling), NCCL all-reduce of the parameter
-gradients (dA, dD, d_delta_bias) every step -- the scan itself has no collective (multi-GPU).
+The metric is quoted at two sequence lengths, so a STEP = one forward + one backward of the selective-scan op at BOTH of them:
+L = 196 (224 x 224 images, 14 x 14 tokens; B = 148 / GPU) and L = 6400 (1280 x 1280, 80 x 80 tokens; B = 16 / GPU), with SS2D's
+shapes (d_inner 768 -> R = 4 x 768 = 3072 scan rows, G = 4 B/C groups, d_state 1 = R2GenCSR's shipped VMamba config).  One
+patch-token = one (image, position) over all R rows; `value` = patch-tokens of both halves / time of both halves (inputs
+resident in HBM).  `--workload NAME` times a single workload instead.  `e2e` goes through the same C-ABI calls but starts from
+pinned HOST buffers and ends with the results back in host memory (copies inside the timed region).
+N > 1 (torchrun): pure data parallelism, per-GPU batch fixed (weak scaling); every step ends with the DDP gradient exchange of
+the model the scan sits in (ARM-Base: 84 M parameters = 0.34 GB fp32, 25 MB buckets, NCCL all-reduce issued asynchronously
+through medical_image_analysis_b200.dp) -- the scan itself has no collective (multi-GPU).
 """
 import argparse
 import json
@@ -30,7 +33,8 @@ WORKLOADS = {
     # (at B = 64 the 5.2 waves of the forward cost 6: -11 %; SURVEY 8d: "B chosen to fill the GPU (e.g. 64-256)")
     "ss2d_m196_n1": dict(B=148, R=3072, G=4, L=196, N=1, out_f32=False),
     "ss2d_m196_n16": dict(B=64, R=3072, G=4, L=196, N=16, out_f32=False),
-    "ss2d_m6400_n1": dict(B=4, R=3072, G=4, L=6400, N=1, out_f32=False),
+    "ss2d_m6400_n1": dict(B=16, R=3072, G=4, L=6400, N=1, out_f32=False),
+    "ss2d_m6400_n1_b4": dict(B=4, R=3072, G=4, L=6400, N=1, out_f32=False),
     "ss2d_m6400_n16": dict(B=4, R=3072, G=4, L=6400, N=16, out_f32=False),
     "ss2d_m196_n1_o32": dict(B=64, R=3072, G=4, L=196, N=1, out_f32=True),
     "ss2d_m196_n16_o32": dict(B=64, R=3072, G=4, L=196, N=16, out_f32=True),
@@ -39,6 +43,8 @@ WORKLOADS = {
     "arm_m197_n16_z": dict(B=64, R=768, G=1, L=197, N=16, out_f32=False, z=True),
 }
 DEFAULT = "ss2d_m196_n1"
+HEADLINE = ("ss2d_m196_n1", "ss2d_m6400_n1")     # the two halves of the metric; the default run times both in every step
+GRAD_BUCKET_PARAMS = 84_000_000                  # ARM-Base / VMamba-B size: the DDP exchange of a real step
 METRIC = "patch-tokens/sec SS2D fwd+bwd at L=196/6400 D=768; % HBM roofline"
 
 
@@ -153,36 +159,43 @@ class ClockSampler:
         return out
 
 
-def run_device_steps(inp, steps, warmup, dist_grads=None):
-    """K timed fwd+bwd steps on resident inputs; returns (total_ms, fwd_ms_avg, bwd_ms_avg)."""
+def run_device_steps(inps, steps, warmup, dist_grads=None):
+    """K timed steps on resident inputs; a step = fwd + bwd of every workload in `inps` (a list), then the gradient exchange.
+    Returns (total_ms, [fwd_ms_avg per workload], [bwd_ms_avg per workload])."""
     from medical_image_analysis_b200 import scan_bwd, scan_fwd
-    out_f32 = inp["dout"].dtype == torch.float32 and inp["u"].dtype != torch.float32
+    if isinstance(inps, dict):
+        inps = [inps]
+    nw = len(inps)
 
     def one(ev=None, last=False):
-        if ev:
-            ev[0].record()
-        z = inp.get("z")
-        out, x, _ = scan_fwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], z, inp["bias"], True, out_f32)
-        if ev:
-            ev[1].record()
-        g = scan_bwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], z, inp["bias"], inp["dout"], x,
-                     out if z is not None else None, True)
+        g = None
+        for wi, inp in enumerate(inps):
+            out_f32 = inp["dout"].dtype == torch.float32 and inp["u"].dtype != torch.float32
+            if ev:
+                ev[3 * wi].record()
+            z = inp.get("z")
+            out, x, _ = scan_fwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], z, inp["bias"], True, out_f32)
+            if ev:
+                ev[3 * wi + 1].record()
+            g = scan_bwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], z, inp["bias"], inp["dout"], x,
+                         out if z is not None else None, True)
+            if ev:
+                ev[3 * wi + 2].record()
         if dist_grads is not None:
             dist_grads(g, last)
         if ev:
-            ev[2].record()
-        return out, g
+            ev[3 * nw].record()
 
     for k in range(warmup):
         one(None, k == warmup - 1)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3 * nw + 1)] for _ in range(steps)]
     torch.cuda.synchronize()
     for k in range(steps):
         one(evs[k], k == steps - 1)
     torch.cuda.synchronize()
-    total = evs[0][0].elapsed_time(evs[-1][2])
-    fwd = sum(e[0].elapsed_time(e[1]) for e in evs) / steps
-    bwd = sum(e[1].elapsed_time(e[2]) for e in evs) / steps
+    total = evs[0][0].elapsed_time(evs[-1][3 * nw])
+    fwd = [sum(e[3 * wi].elapsed_time(e[3 * wi + 1]) for e in evs) / steps for wi in range(nw)]
+    bwd = [sum(e[3 * wi + 1].elapsed_time(e[3 * wi + 2]) for e in evs) / steps for wi in range(nw)]
     return total, fwd, bwd
 
 
@@ -311,6 +324,71 @@ def aux_kernels(dev, peak_gbs, n=20):
     return out
 
 
+def module_timings(dev, peak_gbs, peak_tf, n=10):
+    """Module-level numbers through the autograd surface: fwd + bwd under bf16 autocast, loss = out.float().sum()
+    like the reference's speed test (test_selective_scan_speed.py:511).  tokens/s = images x tokens / time."""
+    from medical_image_analysis_b200.arm import arm_base_pz16
+    from medical_image_analysis_b200.mae import SmallPatchEmbed
+    from medical_image_analysis_b200.vmamba import SS2D
+    out = []
+
+    def timed(step):
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    def fb(m, x):
+        def step():
+            for p in m.parameters():
+                p.grad = None
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = m(x)
+            y.float().sum().backward()
+        return step
+
+    for name, B, H in (("SS2D(d_model=384, ssm_ratio=2, d_state=1, v3noz) 14x14", 64, 14), ("same, 80x80", 4, 80)):
+        try:
+            m = SS2D(d_model=384, ssm_ratio=2.0, d_state=1, forward_type="v3noz").to(dev)
+            x = torch.randn(B, H, H, 384, device=dev, requires_grad=True)
+            ms = timed(fb(m, x))
+            out.append({"module": name, "B": B, "ms_fwd_bwd": ms, "patch_tokens_per_s": B * H * H / (ms * 1e-3)})
+            del m, x
+        except Exception as e:  # report, never hide
+            out.append({"module": name, "error": repr(e)})
+    try:   # BASELINE configs[1]: MambaXray-VL-Base encoder (12 x (4-direction Mamba mixer + SwiGLU), L = 197, D = 768)
+        m = arm_base_pz16(drop_path_rate=0.0).to(dev)
+        x = torch.randn(32, 3, 224, 224, device=dev)
+        ms = timed(fb(m, x))
+        out.append({"module": "arm_base_pz16 encoder fwd+bwd, 224x224 (BASELINE configs[1])", "B": 32, "ms_fwd_bwd": ms,
+                    "patch_tokens_per_s": 32 * 196 / (ms * 1e-3), "images_per_s": 32 / (ms * 1e-3)})
+        del m, x
+    except Exception as e:
+        out.append({"module": "arm_base_pz16", "error": repr(e)})
+    try:   # BASELINE configs[2] patch encode: 17.6 GFLOP forward per 1280 x 1280 image, x3 with the two backward GEMMs
+        B = 8
+        m = SmallPatchEmbed(1, 1024, 1024).to(dev)
+        x = torch.randn(B, 1, 1280, 1280, device=dev)
+        ms = timed(fb(m, x))
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            ms_f = timed(lambda: m(x))
+        fl = 2.0 * B * (6400 * 256 * 1024 + 400 * 16384 * 1024 + 400 * 1024 * 1024)
+        out.append({"module": "SmallPatchEmbed(1, 1024, 1024) 1280x1280 (BASELINE configs[2] patch encode)", "B": B, "ms_fwd": ms_f,
+                    "ms_fwd_bwd": ms, "patch_tokens_per_s": B * 6400 / (ms * 1e-3), "fwd_tflops": fl / ms_f / 1e9,
+                    "fwd_frac_of_measured_bf16_peak": fl / ms_f / 1e9 / peak_tf})
+        del m, x
+    except Exception as e:
+        out.append({"module": "SmallPatchEmbed", "error": repr(e)})
+    torch.cuda.empty_cache()
+    return out
+
+
 def cpu_reference_run(w, steps, warmup, budget_s=150.0):
     """The reference's own CPU algorithm (oracle/selective_scan_ref.py = restatement of selective_scan_ref +
     torch autograd, all host threads) on a BOUNDED sample of the workload: one image (B=1), and if K steps of
@@ -367,27 +445,64 @@ def cpu_reference_run(w, steps, warmup, budget_s=150.0):
     return value, dt * 1e3 / steps, sample, torch.get_num_threads()
 
 
+def _numa_local_affinity(index):
+    """Best effort: run this process (hence first-touch its pinned buffers) on the CPUs of the GPU's NUMA node, so that the e2e
+    copies do not cross the inter-socket link (19.6 vs 44 GB/s between boxes).  Returns a description."""
+    try:
+        bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+        if bus is None:
+            import pynvml as nv
+            nv.nvmlInit()
+            bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(index)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return "numa_node unknown (-1): affinity unchanged"
+        cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return f"pinned to NUMA node {node} ({len(ids)} cpus)"
+        return f"NUMA node {node} has no allowed cpu: affinity unchanged"
+    except Exception as e:
+        return f"affinity unchanged ({type(e).__name__})"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="headline", choices=["headline"] + sorted(WORKLOADS))
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of the workload")
+    ap.add_argument("--no-modules", action="store_true")
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (single-workload runs)")
     args = ap.parse_args()
-    w = dict(WORKLOADS[args.workload])
-    if args.batch > 0:
-        w["B"] = args.batch
+    names = list(HEADLINE) if args.workload == "headline" else [args.workload]
+    ws = [dict(WORKLOADS[n]) for n in names]
+    if args.batch > 0 and len(ws) == 1:
+        ws[0]["B"] = args.batch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    fwd_b, bwd_b = bytes_per_token(w)
-    config = {"workload": f"{args.workload}: selective scan fwd+bwd, B={w['B']}/GPU, R=3072 (K=4 x d_inner 768), G=4, L={w['L']}, "
-                          f"d_state={w['N']}, bf16 in, {'fp32' if w['out_f32'] else 'bf16'} out/dout",
-              "bytes_per_token": fwd_b + bwd_b, "l2": "working set > L2 (no flush needed)", "parallelism": f"dp{world}",
+    bpt = [bytes_per_token(w) for w in ws]
+    tokens = [w["B"] * w["L"] for w in ws]                    # per GPU and step
+    desc = " + ".join(f"{n} (B={w['B']}/GPU, L={w['L']}, d_state={w['N']}{', z gate' if w.get('z') else ''}, bf16 in, "
+                      f"{'fp32' if w['out_f32'] else 'bf16'} out/dout)" for n, w in zip(names, ws))
+    config = {"workload": f"selective scan fwd+bwd, R=3072 (K=4 x d_inner 768), G=4: {desc}" if args.workload == "headline" or ws[0]["R"] == 3072
+              else f"selective scan fwd+bwd: {desc}, R={ws[0]['R']}, G={ws[0]['G']}",
+              "patch_tokens_per_step_per_gpu": sum(tokens), "bytes_per_token": [f + b for f, b in bpt],
+              "l2": "working set > L2 (no flush needed)", "parallelism": f"dp{world}",
+              "grad_exchange": f"{GRAD_BUCKET_PARAMS / 1e6:.0f} M fp32 parameter gradients per step in 25 MB buckets (N > 1)",
               "compute": "fp32 scan arithmetic on bf16 activations (dtype key = arithmetic type)"}
 
     if args.impl == "reference":
@@ -396,11 +511,18 @@ def main():
             return
         steps = max(1, args.steps)
         torch.set_num_threads(os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1: use every host core
-        value, ms, sample, cores = cpu_reference_run(w, steps, max(0, args.warmup))
+        per = []
+        for w in ws:
+            v, ms, sample, cores = cpu_reference_run(w, steps, max(0, args.warmup), budget_s=150.0 / len(ws))
+            per.append((v, ms, sample, cores))
+        # the same token mix as the B200 arm: time per step = sum_i tokens_i / value_i
+        t_step = sum(t / p[0] for t, p in zip(tokens, per))
+        value = sum(tokens) / t_step
+        sample = " | ".join(p[2] for p in per)
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "patch-tokens/s", "n_gpus": args.gpus, "steps": steps,
-                "warmup": max(0, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": max(0, args.warmup), "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": value, "unit": "patch-tokens/s", "cores": cores, "kind": "port", "sample": sample},
+                "cpu_baseline": {"value": value, "unit": "patch-tokens/s", "cores": per[0][3], "kind": "port", "sample": sample},
                 "e2e": {"value": value, "unit": "patch-tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -408,60 +530,46 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (use --impl reference for the CPU arm)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = _numa_local_affinity(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    from medical_image_analysis_b200 import _lib
+    from medical_image_analysis_b200 import _lib, dp
 
-    inp = make_inputs(w, dev, seed=rank)
+    inps = [make_inputs(w, dev, seed=rank + 17 * i) for i, w in enumerate(ws)]
     dist_grads = None
+    exchange = None
     if world > 1:
-        pending = []
+        # DDP's gradient step for the model the scan sits in: ARM-Base-sized fp32 gradients (the scan's own dA / dD / dbias are
+        # its first elements) in 25 MB buckets, all-reduced asynchronously so that they overlap the next step (as DDP
+        # overlaps its buckets with the rest of the backward); the last step's exchange completes inside the timed region
+        exchange = dp.BucketedGradExchange(GRAD_BUCKET_PARAMS, dev, bucket_bytes=25 << 20)
 
         def dist_grads(g, last=False):
-            """DDP's gradient step: one bucket with the parameter gradients (dA, dD, d_delta_bias), all-reduced
-            asynchronously on NCCL's stream so that it overlaps the next step's forward (as DDP overlaps its buckets with
-            the rest of the backward); the previous step's bucket is waited for first, the last one inside the timed region."""
-            for h in pending:
-                h.wait()
-            pending.clear()
-            flat = torch.cat([g[2].flatten(), g[5], g[6]])
-            h = dist.all_reduce(flat, async_op=True)
-            if last:
-                h.wait()
-            else:
-                pending.append(h)
+            exchange.step([g[2], g[5], g[6]], wait=last)
     sampler = ClockSampler(local_rank)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    # warm-up happens inside; the sampler runs across the timed steps
-    launches0 = None
-    from medical_image_analysis_b200 import scan_bwd, scan_fwd  # noqa: F401
     sampler.start()
-    # a short sustained pre-roll so nvidia-smi sees load, then the measured region
-    run_device_steps(inp, max(3, args.warmup), 0, dist_grads)
-    time.sleep(0.02)                       # let the NVML thread come up before the timed region
+    run_device_steps(inps, max(3, args.warmup), 0, dist_grads)          # warm-up (>= 3 steps), also the sustained pre-roll
+    time.sleep(0.02)
     sampler.mark()
     launches0 = _lib.launch_count()
-    total_ms, fwd_ms, bwd_ms = run_device_steps(inp, args.steps, 0, dist_grads)
+    if world > 1:
+        dist.barrier()
+    total_ms, fwd_ms, bwd_ms = run_device_steps(inps, args.steps, 0, dist_grads)
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop()
-    t = torch.tensor([total_ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    tokens_per_step = w["B"] * w["L"] * world
-    value = tokens_per_step * args.steps / (total_ms * 1e-3)
+    total_ms = dp.max_over_ranks(total_ms, dev)
+    value = sum(tokens) * world * args.steps / (total_ms * 1e-3)
 
-    # ---- end to end: host buffers in, host buffers out
+    # ---- end to end: host buffers in, host buffers out (the L = 196 half: the PCIe-bound part is per token the same)
     e2e_steps = max(3, min(args.steps, 10))
-    e2e_ms, h2d, d2h = run_e2e_steps(w, inp, e2e_steps, 2)
-    t = torch.tensor([e2e_ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = tokens_per_step * e2e_steps / (float(t.item()) * 1e-3)
+    e2e_ms, h2d, d2h = run_e2e_steps(ws[0], inps[0], e2e_steps, 2)
+    e2e_ms = dp.max_over_ranks(e2e_ms, dev)
+    e2e_value = tokens[0] * world * e2e_steps / (e2e_ms * 1e-3)
 
     if rank != 0:
         if world > 1:
@@ -469,27 +577,44 @@ def main():
         return
 
     peak, peak_src = peaks()
-    per_gpu_tokens = w["B"] * w["L"]
-    bwd_gbs = per_gpu_tokens * bwd_b / (bwd_ms * 1e-3) / 1e9
-    fwd_gbs = per_gpu_tokens * fwd_b / (fwd_ms * 1e-3) / 1e9
-    step_gbs = (value / world) * (fwd_b + bwd_b) / 1e9
-    roofline = {"bound": "hbm", "kernel": "backward C-ABI call = %s + ss_finalize_kernel (timed together)" % ("ss_bwd_rows_kernel<bf16>" if w["N"] == 1 else "ss_bwd_kernel<bf16>"),
-                "achieved": bwd_gbs, "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak,
-                "traffic": (ncu_traffic("bwd", w["B"])[0] if args.workload == DEFAULT else None), "traffic_source": ncu_traffic("bwd", w["B"])[1],
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": per_gpu_tokens * bwd_b,
-                "fwd_kernel": {"kernel": "forward C-ABI call = %s" % ("ss_fwd_rows_kernel<bf16>" if w["N"] == 1 else "ss_fwd_kernel<bf16>"), "achieved": fwd_gbs, "frac": fwd_gbs / peak,
-                               "algorithmic_bytes_per_launch": per_gpu_tokens * fwd_b},
-                "step": {"achieved": step_gbs, "frac": step_gbs / peak, "roofline_tokens_per_s": peak * 1e9 / (fwd_b + bwd_b)}}
+    peak_tf = 1671.8
+    try:
+        peak_tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        pass
+    per = []
+    for n, w, tk, (fb_, bb_), f_ms, b_ms in zip(names, ws, tokens, bpt, fwd_ms, bwd_ms):
+        fg, bg = tk * fb_ / (f_ms * 1e-3) / 1e9, tk * bb_ / (b_ms * 1e-3) / 1e9
+        per.append({"workload": n, "B": w["B"], "L": w["L"], "d_state": w["N"], "patch_tokens_per_s": tk / ((f_ms + b_ms) * 1e-3),
+                    "fwd_ms": f_ms, "bwd_ms": b_ms, "fwd": {"achieved": fg, "frac": fg / peak, "algorithmic_bytes_per_launch": tk * fb_},
+                    "bwd": {"achieved": bg, "frac": bg / peak, "algorithmic_bytes_per_launch": tk * bb_},
+                    "step_frac": tk * (fb_ + bb_) / ((f_ms + b_ms) * 1e-3) / 1e9 / peak})
+    dom = max(range(len(ws)), key=lambda i: bwd_ms[i])          # dominant kernel = the backward call with the largest time share
+    step_bytes = sum(tk * (f + b) for tk, (f, b) in zip(tokens, bpt))
+    step_gbs = step_bytes / (total_ms / args.steps * 1e-3) / 1e9
+    bwd_kernel = {1: "ss_bwd_rows_kernel<bf16> (or ss_bwd_fast for rows the row-serial kernel does not take)", 16: "ss_bwd_rowsn_kernel<bf16>"}
+    traffic, traffic_src = ncu_traffic("bwd", ws[dom]["B"]) if names[dom] == DEFAULT else (None, None)
+    roofline = {"bound": "hbm",
+                "kernel": "backward C-ABI call of %s = %s + ss_finalize_kernel (timed together, CUDA events in the timed region)"
+                          % (names[dom], bwd_kernel.get(ws[dom]["N"], "ss_bwd_kernel")),
+                "achieved": per[dom]["bwd"]["achieved"], "peak": peak, "unit": "GB/s", "frac": per[dom]["bwd"]["frac"],
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": per[dom]["bwd"]["algorithmic_bytes_per_launch"],
+                "per_workload": per,
+                "step": {"achieved": step_gbs, "frac": step_gbs / peak, "roofline_tokens_per_s": peak * 1e9 * sum(tokens) / step_bytes}}
     line = {"metric": METRIC, "value": value, "unit": "patch-tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": e2e_value, "unit": "patch-tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": "patch-tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "workload": names[0], "host_affinity": numa},
             "roofline": roofline}
+    if exchange is not None:
+        line["grad_exchange"] = exchange.report()
 
     if not args.no_extras and world == 1:
         extras = []
         for name, ww in WORKLOADS.items():
-            if name == args.workload:
+            if name in names:
                 continue
             try:
                 i2 = make_inputs(ww, dev, seed=1)
@@ -497,7 +622,7 @@ def main():
                 tms, f_ms, b_ms = run_device_steps(i2, 10, 0)
                 fb, bb = bytes_per_token(ww)
                 v = ww["B"] * ww["L"] * 10 / (tms * 1e-3)
-                extras.append({"workload": name, "B": ww["B"], "value": v, "ms_per_step": tms / 10, "fwd_ms": f_ms, "bwd_ms": b_ms,
+                extras.append({"workload": name, "B": ww["B"], "value": v, "ms_per_step": tms / 10, "fwd_ms": f_ms[0], "bwd_ms": b_ms[0],
                                "bytes_per_token": fb + bb, "hbm_frac": v * (fb + bb) / 1e9 / peak})
                 del i2
                 torch.cuda.empty_cache()
@@ -508,10 +633,15 @@ def main():
             line["aux_kernels"] = aux_kernels(dev, peak)
         except Exception as e:  # report, never hide
             line["aux_kernels"] = {"error": repr(e)}
+    if not args.no_modules and world == 1:
+        try:
+            line["modules"] = module_timings(dev, peak, peak_tf)
+        except Exception as e:  # report, never hide
+            line["modules"] = {"error": repr(e)}
 
     if not args.no_cpu:
         torch.set_num_threads(os.cpu_count() or 1)
-        cv, cms, sample, cores = cpu_reference_run(w, 2, 0, budget_s=20.0)
+        cv, cms, sample, cores = cpu_reference_run(ws[0], 2, 0, budget_s=20.0)
         line["cpu_baseline"] = {"value": cv, "unit": "patch-tokens/s", "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(line))
     if world > 1:

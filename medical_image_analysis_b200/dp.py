@@ -43,3 +43,44 @@ def shard_batch(global_batch: int, rank: int, world: int) -> range:
     base, rem = divmod(global_batch, world)
     lo = rank * base + min(rank, rem)
     return range(lo, lo + base + (1 if rank < rem else 0))
+
+
+class BucketedGradExchange:
+    """DDP's gradient step without DDP: a flat fp32 gradient buffer of `n_params` elements cut into `bucket_bytes` buckets
+    (torch DDP's default is 25 MB), each all-reduced asynchronously on NCCL's stream.  ``step(grads)`` copies the given
+    gradient tensors into the head of the buffer (the rest stands for the other parameters of the model the scan sits in),
+    waits for the PREVIOUS step's buckets (they overlapped this step's compute, as DDP overlaps buckets with the rest of
+    the backward) and launches this step's; ``wait=True`` also completes them (last step / optimizer boundary)."""
+
+    def __init__(self, n_params: int, device, bucket_bytes: int = 25 << 20, group=None):
+        self.flat = torch.zeros(n_params, dtype=torch.float32, device=device)
+        per = max(1, bucket_bytes // 4)
+        self.buckets = [self.flat[i:i + per] for i in range(0, n_params, per)]
+        self.group, self.pending = group, []
+        self.bytes_per_step = n_params * 4
+        self.steps = 0
+
+    def drain(self):
+        for h in self.pending:
+            h.wait()
+        self.pending.clear()
+
+    def step(self, grads, wait: bool = False):
+        self.drain()
+        off = 0
+        for g in grads:
+            if g is None:
+                continue
+            n = g.numel()
+            self.flat[off:off + n].copy_(g.reshape(-1))
+            off += n
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            self.pending = [dist.all_reduce(b, group=self.group, async_op=True) for b in self.buckets]
+        self.steps += 1
+        if wait:
+            self.drain()
+
+    def report(self):
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        return {"bytes_per_step": self.bytes_per_step, "buckets": len(self.buckets), "world": world,
+                "note": "all-reduce bus traffic per rank = 2 (n-1)/n x bytes_per_step; overlapped with the next step's kernels"}

