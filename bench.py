@@ -174,11 +174,12 @@ def run_device_steps(inps, steps, warmup, dist_grads=None):
             if ev:
                 ev[3 * wi].record()
             z = inp.get("z")
-            out, x, _ = scan_fwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], z, inp["bias"], True, out_f32)
+            out, x, _, hblk = scan_fwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], z, inp["bias"], True, out_f32,
+                                       want_block_states=True)
             if ev:
                 ev[3 * wi + 1].record()
             g = scan_bwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], z, inp["bias"], inp["dout"], x,
-                         out if z is not None else None, True)
+                         out if z is not None else None, True, hblk=hblk)
             if ev:
                 ev[3 * wi + 2].record()
         if dist_grads is not None:
@@ -235,8 +236,9 @@ def run_e2e_steps(w, inp, steps, warmup, n_slices=4):
             with torch.cuda.stream(s_cmp):
                 s_cmp.wait_event(ev_in)
                 sl = {k: dev_in[k][lo:hi] for k in names}
-                out, x, _ = scan_fwd(sl["u"], sl["delta"], inp["A"], sl["B"], sl["C"], inp["D"], None, inp["bias"], True, out_f32)
-                g = scan_bwd(sl["u"], sl["delta"], inp["A"], sl["B"], sl["C"], inp["D"], None, inp["bias"], sl["dout"], x, None, True)
+                out, x, _, hblk = scan_fwd(sl["u"], sl["delta"], inp["A"], sl["B"], sl["C"], inp["D"], None, inp["bias"], True, out_f32,
+                                           want_block_states=True)
+                g = scan_bwd(sl["u"], sl["delta"], inp["A"], sl["B"], sl["C"], inp["D"], None, inp["bias"], sl["dout"], x, None, True, hblk=hblk)
                 res = [out] + [t for t in g if t is not None]
                 ev_cmp.record()
             prev_cmp[si] = ev_cmp

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MIA_ABI_VERSION 1
+#define MIA_ABI_VERSION 2
 
 enum { MIA_F32 = 0, MIA_F16 = 1, MIA_BF16 = 2 };
 
@@ -96,6 +96,13 @@ typedef struct mia_ss_params {
     /* ---- scratch for the deterministic reductions of the backward (f32 partials) */
     void *workspace;
     size_t workspace_bytes;
+
+    /* ---- (ABI 2) optional block states handed from fwd to the matching bwd: mia_ss_block_state_floats(p) floats, 128-byte
+     * aligned, or NULL.  The d_state == 1 row-serial forward kernels write the state entering every 16-token block of
+     * every row here (when mia_ss_fwd_writes_block_states(p) != 0); given to the backward of the SAME inputs it lets the
+     * windowed kernel (csrc/scan_bwd_win.cuh) skip the forward recompute pass.  NULL on either side = the resident-row /
+     * warp-scan kernels, same results. */
+    float *hblk;
 } mia_ss_params;
 
 /* ABI / build identification. */
@@ -105,6 +112,11 @@ const char *mia_last_error(void);
 /* Checkpoint geometry: tokens per chunk for a sequence length, and ceil(seqlen / chunk). */
 int mia_ss_chunk_len(int seqlen);
 int mia_ss_num_chunks(int seqlen);
+
+/* Block states (see mia_ss_params.hblk): size in floats for these sizes, and whether the forward for exactly these
+ * parameters (pointers, strides, dtypes) will fill p->hblk (0 when the shape takes a kernel that does not produce them). */
+size_t mia_ss_block_state_floats(const mia_ss_params *p);
+int mia_ss_fwd_writes_block_states(const mia_ss_params *p);
 
 /* Forward.  Replaces selective_scan_fwd (selective_scan_oflex.cpp:143-231). */
 int mia_selective_scan_fwd(const mia_ss_params *p, void *cuda_stream);

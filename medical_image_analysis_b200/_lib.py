@@ -32,7 +32,7 @@ class MiaSSParams(ctypes.Structure):
         + [(n, _i64) for n in ("du_batch_stride", "du_d_stride", "ddelta_batch_stride", "ddelta_d_stride",
                                "dA_d_stride", "dA_dstate_stride", "dB_batch_stride", "dB_group_stride", "dB_dstate_stride",
                                "dC_batch_stride", "dC_group_stride", "dC_dstate_stride", "dz_batch_stride", "dz_d_stride")]
-        + [("workspace", _vp), ("workspace_bytes", ctypes.c_size_t)]
+        + [("workspace", _vp), ("workspace_bytes", ctypes.c_size_t), ("hblk", _vp)]
     )
 
 
@@ -80,8 +80,12 @@ def lib() -> ctypes.CDLL:
         L.mia_gemm_tn.argtypes = [_vp, _vp, _vp, _vp, ci, ci, ci, ll, ll, ll, ci, ci, ci, _vp]
         L.mia_gemm_tn.restype = ci
         L.mia_gemm_last_error.restype = ctypes.c_char_p
-        if L.mia_abi_version() != 1:
-            raise RuntimeError(f"libmia_scan.so ABI version {L.mia_abi_version()} != 1: rebuild it")
+        L.mia_ss_block_state_floats.argtypes = [ctypes.POINTER(MiaSSParams)]
+        L.mia_ss_block_state_floats.restype = ctypes.c_size_t
+        L.mia_ss_fwd_writes_block_states.argtypes = [ctypes.POINTER(MiaSSParams)]
+        L.mia_ss_fwd_writes_block_states.restype = ctypes.c_int
+        if L.mia_abi_version() != 2:
+            raise RuntimeError(f"libmia_scan.so ABI version {L.mia_abi_version()} != 2: rebuild it")
         _lib = L
     return _lib
 

@@ -220,12 +220,29 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
                         tc_ld32(taddr + (uint32_t)(c * cc + hlf * 32), r);
                         tc_wait_ld();
                         float v[32];
+                        const int cb = col0 + hlf * 32;
+                        if (g.has_bias) {
+                            if (cb + 32 <= g.N && ((reinterpret_cast<uintptr_t>(g.bias + cb) & 15) == 0)) {   // 8 x 16-byte loads
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            v[j] = __uint_as_float(r[j]);
-                            const int col = col0 + hlf * 32 + j;
-                            if (g.has_bias) v[j] += (col < g.N) ? __ldg(g.bias + col) : 0.f;
-                            v[j] = act_apply(v[j], g.act);
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 b4 = __ldg(reinterpret_cast<const float4 *>(g.bias + cb) + j);
+                                    v[4 * j] = __uint_as_float(r[4 * j]) + b4.x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
+                                    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + ((cb + j < g.N) ? __ldg(g.bias + cb + j) : 0.f);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                        }
+                        if (g.act == MIA_ACT_RELU) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                        } else if (g.act != MIA_ACT_NONE) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], g.act);
                         }
                         if (g.out_f32) {
 #pragma unroll

@@ -11,6 +11,7 @@
 #include "scan_common.cuh"
 #include "scan_bwd_rows.cuh"
 #include "scan_bwd_rowsn.cuh"
+#include "scan_bwd_win.cuh"
 #include "scan_fwd_rowsn.cuh"
 #include "scan_fwd_stream.cuh"
 #include "scan_fwd_chunks.cuh"
@@ -22,6 +23,7 @@ template <typename T> cudaError_t launch_fwd_stream(const StreamArgs &, int, boo
 template <typename T> cudaError_t launch_fwd_chunks(const ChunkArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_rows(const RowsBwdArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_rowsn(const RowsNBwdArgs &, int, bool, cudaStream_t);
+template <typename T> cudaError_t launch_bwd_win(const WinBwdArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_fwd_any(const ScanArgs &, int, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_any(const ScanArgs &, int, cudaStream_t);
 }  // namespace mia
@@ -309,6 +311,7 @@ bool plan_rows_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsArgs &
     if (r.smem_bytes > di.smem_optin) return false;
     r.xchunks = mia_ss_num_chunks(L); r.xchunk_tokens = mia_ss_chunk_len(L);
     r.u = p.u; r.delta = p.delta; r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.out = p.out; r.x = p.x;
+    r.hblk = p.hblk; r.nblk16 = (L + 15) / 16;
     r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride;
     const int per_sm = di.smem_optin / (r.smem_bytes + 1024) > 0 ? (227 * 1024) / (r.smem_bytes + 1024) : 1;
     grid = di.sms * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
@@ -343,6 +346,7 @@ bool plan_chunks_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::ChunkArg
     if (per_sm < 3) return false;
     if (per_sm > 8) per_sm = 8;
     r.u = p.u; r.delta = p.delta; r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.out = p.out; r.x = p.x;
+    r.hblk = p.hblk; r.nblk16 = (L + 15) / 16;
     r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride;
     grid = di.sms * per_sm;
     if (grid > r.n_items) grid = r.n_items;
@@ -464,6 +468,45 @@ bool plan_rows_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsBwdArg
     // phase 2 -> store), so this path only wins while every item gets its own resident CTA (measured on B200, L = 6400:
     // 546 vs 734 us at 0.65 items per slot, 1076 vs 1123 us at 1.3, 2017 vs 1769 us at 2.6).
     if (nch > 1 && r.n_items > grid) return false;
+    if (grid > r.n_items) grid = r.n_items;
+    return true;
+}
+
+// Windowed row-serial backward on forward-provided block states (scan_bwd_win.cuh): eligibility + argument block.
+bool plan_win_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::WinBwdArgs &r, int &grid) {
+    const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
+    const int rpg = p.dim / p.n_groups;
+    if (!p.hblk || p.dstate != 1 || p.z || p.delta_dim != p.dim || (rpg % 32) || (L % 4)) return false;
+    if (dbg_knob("MIA_NO_WIN_BWD")) return false;
+    auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
+    if (!dense(p.u_batch_stride, p.u_d_stride) || !dense(p.delta_batch_stride, p.delta_d_stride) ||
+        !dense(p.dout_batch_stride, p.dout_d_stride) || !dense(p.du_batch_stride, p.du_d_stride) ||
+        !dense(p.ddelta_batch_stride, p.ddelta_d_stride)) return false;
+    if (p.A_d_stride != 1 && p.dim > 1) return false;
+    if (((uintptr_t)p.u | (uintptr_t)p.delta | (uintptr_t)p.dout | (uintptr_t)p.du | (uintptr_t)p.ddelta | (uintptr_t)p.B | (uintptr_t)p.C) & 7)
+        return false;
+    if (((p.B_batch_stride | p.B_group_stride | p.C_batch_stride | p.C_group_stride) * es) % 8) return false;   // 8-byte B / C pieces
+    memset(&r, 0, sizeof(r));
+    r.batch = p.batch; r.dim = p.dim; r.L = L; r.G = p.n_groups; r.rows_per_group = rpg; r.softplus = p.delta_softplus;
+    r.n_items = p.batch * p.n_groups * (rpg / 32);
+    r.nblk = (L + mia::kBlk - 1) / mia::kBlk;
+    r.nwin = (L + mia::kWinTok - 1) / mia::kWinTok;
+    r.pitch = mia::kWinTok * es + 8;
+    r.pitcho = mia::kWinTok * eo + 8;
+    r.off_u = 0;
+    r.off_d = round_up(32 * r.pitch, 16);
+    r.off_o = 2 * r.off_d;
+    r.off_bcraw = r.off_o + round_up(32 * r.pitcho, 16);
+    r.stage_bytes = round_up(r.off_bcraw + 2 * mia::kWinTok * es, 128);
+    r.off_bc32 = 2 * r.stage_bytes;
+    r.smem_bytes = r.off_bc32 + 2 * mia::kWinTok * 4;
+    r.u = p.u; r.delta = p.delta; r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.dout = p.dout;
+    r.hblk = p.hblk; r.du = p.du; r.ddelta = p.ddelta;
+    r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride;
+    int per_sm = (227 * 1024) / (r.smem_bytes + 1024);
+    if (per_sm > 12) per_sm = 12;                               // 32 threads x 168 registers
+    if (per_sm < 1) return false;
+    grid = di.sms * per_sm;
     if (grid > r.n_items) grid = r.n_items;
     return true;
 }
@@ -638,6 +681,23 @@ int mia_ss_num_chunks(int seqlen) {
     return (seqlen + ch - 1) / ch;
 }
 
+size_t mia_ss_block_state_floats(const mia_ss_params *pp) {
+    if (!pp || validate_sizes(*pp) != MIA_OK) return 0;
+    const mia_ss_params &p = *pp;
+    if (p.dstate != 1 || ((p.dim / p.n_groups) % 32)) return 0;
+    return (size_t)p.batch * p.dim * ((p.seqlen + 15) / 16);
+}
+
+int mia_ss_fwd_writes_block_states(const mia_ss_params *pp) {
+    if (!pp || !pp->hblk || validate_sizes(*pp) != MIA_OK || !pp->u || !pp->delta || !pp->out) return 0;
+    DeviceInfo di;
+    if (device_info(di) != MIA_OK) return 0;
+    mia::ChunkArgs rc;
+    mia::RowsArgs rr;
+    int grid = 0;
+    return (plan_chunks_fwd(*pp, di, rc, grid) || plan_rows_fwd(*pp, di, rr, grid)) ? 1 : 0;   // the two kernels that fill hblk
+}
+
 int mia_selective_scan_fwd(const mia_ss_params *pp, void *cuda_stream) {
     if (!pp) return fail(MIA_EINVAL, "null params");
     const mia_ss_params &p = *pp;
@@ -769,8 +829,17 @@ int mia_selective_scan_bwd(const mia_ss_params *pp, void *cuda_stream) {
     }
     int rc = 0, bc_parts = pl.split;
     mia::RowsBwdArgs rb;
+    mia::WinBwdArgs wb;
     int rgrid = 0;
-    if (use_rowsn) {
+    if (!use_rowsn && plan_win_bwd(p, di, wb, rgrid)) {
+        wb.part_dA = a.part_dA; wb.part_dD = a.part_dD; wb.part_dbias = a.part_dbias; wb.acc_dB = a.acc_dB; wb.acc_dC = a.acc_dC;
+        bc_parts = wb.rows_per_group / 32;
+        const bool of32 = p.otype == MIA_F32 && p.itype != MIA_F32;
+        rc = dispatch(p.itype, [&](auto *tag) {
+            using T = typename std::remove_pointer<decltype(tag)>::type;
+            return (int)mia::launch_bwd_win<T>(wb, rgrid, of32, stream);
+        });
+    } else if (use_rowsn) {
         rn.part_dA = a.part_dA; rn.part_dD = a.part_dD; rn.part_dbias = a.part_dbias; rn.acc_dB = a.acc_dB; rn.acc_dC = a.acc_dC;
         bc_parts = rn.max_parts;
         const bool of32 = p.otype == MIA_F32 && p.itype != MIA_F32;

@@ -76,8 +76,10 @@ def _stream(t: torch.Tensor) -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
-def scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, out_float=False):
-    """-> (out, x, out_z|None).  out = y + D*u (before the gate), x = (batch, dim, n_chunks, 2*dstate) f32."""
+def scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, out_float=False, want_block_states=False):
+    """-> (out, x, out_z|None) [+ hblk|None when want_block_states].  out = y + D*u (before the gate), x = (batch, dim,
+    n_chunks, 2*dstate) f32.  hblk: the d_state == 1 row-serial forward's per-16-token block states (mia_ss_params.hblk);
+    pass it to scan_bwd(..., hblk=...) of the same inputs and the backward skips its forward recompute pass."""
     batch, dim, L, N, G, ddim = _check_inputs(u, delta, A, B, C, D, delta_bias, z)
     otype = torch.float32 if out_float else u.dtype
     with torch.cuda.device(u.device):
@@ -91,12 +93,21 @@ def scan_fwd(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=
         if out_z is not None:
             p.out_z = out_z.data_ptr()
             p.out_z_batch_stride, p.out_z_d_stride = out_z.stride(0), out_z.stride(1)
+        hblk = None
+        if want_block_states:
+            nfl = int(_lib.lib().mia_ss_block_state_floats(ctypes.byref(p)))
+            if nfl > 0:
+                hblk = torch.empty((nfl,), dtype=torch.float32, device=u.device)
+                p.hblk = hblk.data_ptr()
+                if not _lib.lib().mia_ss_fwd_writes_block_states(ctypes.byref(p)):
+                    hblk, p.hblk = None, None            # this shape takes a kernel that does not produce them
         _lib.check(_lib.lib().mia_selective_scan_fwd(ctypes.byref(p), _stream(u)), "selective_scan_fwd")
-    return out, x, out_z
+    return (out, x, out_z, hblk) if want_block_states else (out, x, out_z)
 
 
-def scan_bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, out, delta_softplus):
-    """-> (du, ddelta, dA, dB, dC, dD|None, ddelta_bias|None, dz|None); ddelta has delta's shape."""
+def scan_bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, out, delta_softplus, hblk=None):
+    """-> (du, ddelta, dA, dB, dC, dD|None, ddelta_bias|None, dz|None); ddelta has delta's shape.  hblk: block states of
+    the matching scan_fwd(..., want_block_states=True), or None."""
     batch, dim, L, N, G, ddim = _check_inputs(u, delta, A, B, C, D, delta_bias, z)
     _req(dout.is_cuda and tuple(dout.shape) == (batch, dim, L), "dout must have shape (batch_size, dim, seqlen)")
     _req(dout.dtype == u.dtype or dout.dtype == torch.float32, "dout must have u's dtype or float32")   # oflex.cpp:248
@@ -123,6 +134,10 @@ def scan_bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, out, delta_softplus):
         p = _lib.MiaSSParams()
         _fill_inputs(p, u, delta, A, B, C, D, delta_bias, z, delta_softplus, dout.dtype)
         p.x = _ptr(x)
+        if hblk is not None:
+            _req(hblk.dtype == torch.float32 and hblk.is_cuda and hblk.is_contiguous(), "hblk must be the float32 tensor scan_fwd returned")
+            p.hblk = hblk.data_ptr()
+            _req(hblk.numel() == int(_lib.lib().mia_ss_block_state_floats(ctypes.byref(p))), "hblk does not belong to these sizes")
         p.dout, p.dout_batch_stride, p.dout_d_stride = dout.data_ptr(), dout.stride(0), dout.stride(1)
         if z is not None:
             p.out_saved, p.out_saved_batch_stride, p.out_saved_d_stride = out.data_ptr(), out.stride(0), out.stride(1)

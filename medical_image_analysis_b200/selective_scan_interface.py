@@ -30,17 +30,18 @@ class SelectiveScanOflex(torch.autograd.Function):
     def forward(ctx, u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1, backnrows=1, oflex=True):
         ctx.delta_softplus = delta_softplus
         out, x, *rest = selective_scan_cuda_oflex.fwd(u, delta, A, B, C, D, delta_bias, delta_softplus, 1, oflex)
-        ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, x)
+        ctx.has_hblk = len(rest) > 0                       # block states for the windowed backward (scan_bwd_win.cuh)
+        ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, x, *rest[:1])
         return out
 
     @staticmethod
     @_bwd
     def backward(ctx, dout, *args):
-        u, delta, A, B, C, D, delta_bias, x = ctx.saved_tensors
+        u, delta, A, B, C, D, delta_bias, x, *hb = ctx.saved_tensors
         if dout.stride(-1) != 1:
             dout = dout.contiguous()
         du, ddelta, dA, dB, dC, dD, ddelta_bias, *rest = selective_scan_cuda_oflex.bwd(
-            u, delta, A, B, C, D, delta_bias, dout, x, ctx.delta_softplus, 1)
+            u, delta, A, B, C, D, delta_bias, dout, x, ctx.delta_softplus, 1, hblk=(hb[0] if hb else None))
         return (du, ddelta, dA, dB, dC, dD, ddelta_bias, None, None, None, None)
 
 
@@ -52,17 +53,18 @@ class SelectiveScanCore(torch.autograd.Function):
     def forward(ctx, u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1, backnrows=1, oflex=True):
         ctx.delta_softplus = delta_softplus
         out, x, *rest = selective_scan_cuda_core.fwd(u, delta, A, B, C, D, delta_bias, delta_softplus, 1)
-        ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, x)
+        ctx.has_hblk = len(rest) > 0                       # block states for the windowed backward (scan_bwd_win.cuh)
+        ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, x, *rest[:1])
         return out
 
     @staticmethod
     @_bwd
     def backward(ctx, dout, *args):
-        u, delta, A, B, C, D, delta_bias, x = ctx.saved_tensors
+        u, delta, A, B, C, D, delta_bias, x, *hb = ctx.saved_tensors
         if dout.stride(-1) != 1:
             dout = dout.contiguous()
         du, ddelta, dA, dB, dC, dD, ddelta_bias, *rest = selective_scan_cuda_core.bwd(
-            u, delta, A, B, C, D, delta_bias, dout, x, ctx.delta_softplus, 1)
+            u, delta, A, B, C, D, delta_bias, dout, x, ctx.delta_softplus, 1, hblk=(hb[0] if hb else None))
         return (du, ddelta, dA, dB, dC, dD, ddelta_bias, None, None, None, None)
 
 

@@ -55,7 +55,7 @@ def test_struct_layout_matches_header(tmp_path):
 
 def test_chunk_geometry():
     lib = _lib()
-    assert lib.mia_abi_version() == 1
+    assert lib.mia_abi_version() == 2
     for L, (ch, n) in {1: (32, 1), 49: (64, 1), 128: (128, 1), 129: (256, 1), 196: (256, 1), 197: (256, 1), 256: (256, 1),
                        257: (256, 2), 6400: (256, 25)}.items():
         assert lib.mia_ss_chunk_len(L) == ch and lib.mia_ss_num_chunks(L) == n, L

@@ -48,8 +48,8 @@ def _run_case(batch, dim, L, N, G, ddim, has_D, has_z, has_bias, softplus, dtype
     fs = long_row_scale(L)
     tag = f"[b{batch} d{dim} L{L} N{N} G{G} dd{ddim} D{int(has_D)} z{int(has_z)} bias{int(has_bias)} sp{int(softplus)} {str(dtype)[6:]} o32={int(out_float)}]"
     cpu, gpu = _inputs(seed, batch, dim, L, N, G, ddim, has_D, has_z, has_bias, dtype)
-    out, x, out_z = scan_fwd(gpu["u"], gpu["delta"], gpu["A"], gpu["B"], gpu["C"], gpu["D"], gpu["z"], gpu["delta_bias"],
-                             softplus, out_float)
+    out, x, out_z, hblk = scan_fwd(gpu["u"], gpu["delta"], gpu["A"], gpu["B"], gpu["C"], gpu["D"], gpu["z"], gpu["delta_bias"],
+                                   softplus, out_float, want_block_states=True)
     r_out, r_out_z, r_last = ss_ref_c.fwd(cpu["u"], cpu["delta"], cpu["A"], cpu["B"], cpu["C"], cpu["D"], cpu["z"],
                                           cpu["delta_bias"], softplus)
     lowp = dtype != torch.float32
@@ -60,16 +60,19 @@ def _run_case(batch, dim, L, N, G, ddim, has_D, has_z, has_bias, softplus, dtype
     cmp_auto(x[:, :, -1, 1::2], r_last, tag + " last_state", f32_scale=fs)
 
     dout = gpu["dout"].float() if out_float else gpu["dout"]
-    du, dd, dA, dB, dC, dD, dbias, dz = scan_bwd(gpu["u"], gpu["delta"], gpu["A"], gpu["B"], gpu["C"], gpu["D"], gpu["z"],
-                                                 gpu["delta_bias"], dout, x, out if has_z else None, softplus)
     ref = ss_ref_c.bwd(cpu["u"], cpu["delta"], cpu["A"], cpu["B"], cpu["C"], cpu["D"], cpu["z"], cpu["delta_bias"],
                        cpu["dout"], softplus)
     # with z the CUDA path reads the saved `out` ROUNDED to the output dtype (like mamba_ssm does): dz = dout out (...)
     # inherits that rounding (half an ulp) on top of its own -> 2 ulp for dz in that configuration only
     dz_ulp = 2.0 if (has_z and lowp and not out_float) else 1.0
-    for name, got in (("du", du), ("ddelta", dd), ("dB", dB), ("dC", dC), ("dz", dz), ("dA", dA), ("dD", dD), ("ddelta_bias", dbias)):
-        if got is not None:
-            cmp_auto(got, ref[name], f"{tag} {name}", n_ulp=dz_ulp if name == "dz" else 1.0, f32_scale=fs)
+    # both backward families: without the forward's block states (resident-row / warp-scan kernels) and, where the forward
+    # produced them (d_state 1 row-serial shapes), with them (windowed kernel, scan_bwd_win.cuh)
+    for path, hb in (("", None),) + ((("[hblk]", hblk),) if hblk is not None else ()):
+        du, dd, dA, dB, dC, dD, dbias, dz = scan_bwd(gpu["u"], gpu["delta"], gpu["A"], gpu["B"], gpu["C"], gpu["D"], gpu["z"],
+                                                     gpu["delta_bias"], dout, x, out if has_z else None, softplus, hblk=hb)
+        for name, got in (("du", du), ("ddelta", dd), ("dB", dB), ("dC", dC), ("dz", dz), ("dA", dA), ("dD", dD), ("ddelta_bias", dbias)):
+            if got is not None:
+                cmp_auto(got, ref[name], f"{tag}{path} {name}", n_ulp=dz_ulp if name == "dz" else 1.0, f32_scale=fs)
 
 
 SMALL = [
@@ -218,8 +221,11 @@ def test_scan_m196_full_wave_batch_spot_rows():
     from tests.parity import cmp_auto
     B, R, G, L, N = 148, 3072, 4, 196, 1
     cpu, gpu = _inputs(31, B, R, L, N, G, R, True, False, True, torch.bfloat16)
-    out, x, _ = scan_fwd(gpu["u"], gpu["delta"], gpu["A"], gpu["B"], gpu["C"], gpu["D"], None, gpu["delta_bias"], True, False)
-    grads = scan_bwd(gpu["u"], gpu["delta"], gpu["A"], gpu["B"], gpu["C"], gpu["D"], None, gpu["delta_bias"], gpu["dout"], x, None, True)
+    out, x, _, hblk = scan_fwd(gpu["u"], gpu["delta"], gpu["A"], gpu["B"], gpu["C"], gpu["D"], None, gpu["delta_bias"], True, False,
+                               want_block_states=True)
+    assert hblk is not None                                      # bench.py's path: the windowed backward on the forward's block states
+    grads = scan_bwd(gpu["u"], gpu["delta"], gpu["A"], gpu["B"], gpu["C"], gpu["D"], None, gpu["delta_bias"], gpu["dout"], x, None, True,
+                     hblk=hblk)
     for b in (0, 73, 147):
         sl = {k: (v[b:b + 1] if (v is not None and v.dim() >= 3) else v) for k, v in cpu.items()}
         r_out, _, r_last = ss_ref_c.fwd(sl["u"], sl["delta"], sl["A"], sl["B"], sl["C"], sl["D"], None, sl["delta_bias"], True)
@@ -244,12 +250,15 @@ def test_scan_strided_inputs():
     _cmp(out, r_out, 1e-5, 2e-5 * max(1.0, r_out.abs().max().item()), "out")
 
 
-def test_bwd_is_deterministic_dstate1():
+@pytest.mark.parametrize("use_hblk", [False, True])
+def test_bwd_is_deterministic_dstate1(use_hblk):
     from medical_image_analysis_b200 import scan_bwd, scan_fwd
     _, g = _inputs(9, 4, 96, 300, 1, 2, 96, True, False, True, torch.bfloat16)
-    out, x, _ = scan_fwd(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], None, g["delta_bias"], True, True)
-    a = scan_bwd(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], None, g["delta_bias"], g["dout"].float(), x, None, True)
-    b = scan_bwd(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], None, g["delta_bias"], g["dout"].float(), x, None, True)
+    out, x, _, hblk = scan_fwd(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], None, g["delta_bias"], True, True, want_block_states=True)
+    assert hblk is not None
+    hb = hblk if use_hblk else None
+    a = scan_bwd(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], None, g["delta_bias"], g["dout"].float(), x, None, True, hblk=hb)
+    b = scan_bwd(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], None, g["delta_bias"], g["dout"].float(), x, None, True, hblk=hb)
     for ta, tb in zip(a, b):
         if ta is not None:
             assert torch.equal(ta, tb)
