@@ -451,15 +451,20 @@ def _numa_local_affinity(index):
     """Best effort: run this process (hence first-touch its pinned buffers) on the CPUs of the GPU's NUMA node, so that the e2e
     copies do not cross the inter-socket link (19.6 vs 44 GB/s between boxes).  Returns a description."""
     try:
-        bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
-        if bus is None:
+        bus = None
+        try:
+            pr = torch.cuda.get_device_properties(index)
+            bus = "%04x:%02x:%02x.0" % (int(pr.pci_domain_id), int(pr.pci_bus_id), int(pr.pci_device_id))
+        except Exception:
             import pynvml as nv
             nv.nvmlInit()
-            bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(index)).busId
-            bus = bus.decode() if isinstance(bus, bytes) else bus
-        bus = bus.lower()
-        if len(bus.split(":")[0]) == 8:
-            bus = bus[4:]
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            info = nv.nvmlDeviceGetPciInfo(h)
+            raw = getattr(info, "busId", None) or getattr(info, "busIdLegacy")
+            bus = (raw.decode() if isinstance(raw, bytes) else str(raw)).lower()
+            if len(bus.split(":")[0]) == 8:
+                bus = bus[4:]
         node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
         if node < 0:
             return "numa_node unknown (-1): affinity unchanged"

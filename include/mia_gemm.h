@@ -28,6 +28,15 @@ enum { MIA_GEMM_OK = 0, MIA_GEMM_EINVAL = -1, MIA_GEMM_ECUDA = -2 };
 
 int mia_gemm_tn(const void *A, const void *W, const float *bias, void *C, int M, int N, int K, long long lda, long long ldw,
                 long long ldc, int in_dtype, int out_dtype, int act, void *cuda_stream);
+/* General form: each operand may also be stored with its M / N index contiguous ("MN-major"), which is what the two
+ * backward contractions of a linear layer need with NO transposed copies:
+ *   a_mn_major = 0: A is [M][K] (pitch lda)      a_mn_major = 1: A is stored [K][M] (pitch lda), i.e. A^T read in place
+ *   b_mn_major = 0: B is [N][K] (pitch ldb)      b_mn_major = 1: B is stored [K][N] (pitch ldb)
+ *   dX[tok, in]  = dY[tok, out] . W[out, in]      -> A = dY (0),            B = W stored [K = out][N = in]   (1)
+ *   dW[out, in]  = dY[tok, out]^T . X[tok, in]    -> A = dY stored [K][M] (1), B = X stored [K = tok][N = in] (1)
+ * The tcgen05 instruction descriptor's a_major / b_major bits select the layout; TMA boxes are [64 k][64 mn] for it. */
+int mia_gemm(const void *A, const void *B, const float *bias, void *C, int M, int N, int K, long long lda, long long ldb, long long ldc,
+             int a_mn_major, int b_mn_major, int in_dtype, int out_dtype, int act, void *cuda_stream);
 const char *mia_gemm_last_error(void);
 
 #ifdef __cplusplus

@@ -134,7 +134,11 @@ int mia_selective_scan_bwd(const mia_ss_params *p, void *cuda_stream);
  * Any H, W: planes are staged in shared memory while one fits (H W <= ~50 K elements), gathered directly beyond. */
 int mia_cross_scan(const void *x, void *xs, int batch, int channels, int H, int W, int dtype, void *cuda_stream);
 int mia_cross_merge(const void *ys, void *y, int batch, int channels, int H, int W, int dtype, void *cuda_stream);
-const char *mia_cs_last_error(void);   /* message of the last failed mia_cross_scan / mia_cross_merge on this thread */
+const char *mia_cs_last_error(void);   /* message of the last failed mia_cross_scan / mia_cross_merge / mia_silu_gate on this thread */
+
+/* out_z[i] = out[i] * silu(z[i]) over n contiguous elements (fp32 arithmetic): the gate of the mamba_ssm signature recomputed
+ * from the saved pre-gate output -- selective_scan_cuda.bwd(..., recompute_out_z=True), test_selective_scan.py:105-108. */
+int mia_silu_gate(const void *out, const void *z, void *out_z, long long n, int z_dtype, int out_dtype, void *cuda_stream);
 
 /* Depth-wise causal conv1d (+ bias, + SiLU) of the Mamba mixers: y[b, d, t] = act(bias[d] + sum_k w[d, k] x[b, d, t - (K-1) + k]).
  * Replaces causal_conv1d.causal_conv1d_fn (un-vendored; call sites arm/Finetuning/mamba_simple.py:676-681 of the three ARM sub-projects) == the in-repo

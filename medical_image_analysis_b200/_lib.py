@@ -66,6 +66,8 @@ def lib() -> ctypes.CDLL:
             fn.argtypes = [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]
             fn.restype = ctypes.c_int
         L.mia_cs_last_error.restype = ctypes.c_char_p
+        L.mia_silu_gate.argtypes = [_vp, _vp, _vp, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, _vp]
+        L.mia_silu_gate.restype = ctypes.c_int
         ll, ci = ctypes.c_longlong, ctypes.c_int
         L.mia_causal_conv1d_fwd.argtypes = [_vp, _vp, _vp, _vp, ci, ci, ci, ci, ci, ci, ll, ll, ll, ll, _vp]
         L.mia_causal_conv1d_fwd.restype = ci
@@ -79,6 +81,8 @@ def lib() -> ctypes.CDLL:
         L.mia_dwconv2d_last_error.restype = ctypes.c_char_p
         L.mia_gemm_tn.argtypes = [_vp, _vp, _vp, _vp, ci, ci, ci, ll, ll, ll, ci, ci, ci, _vp]
         L.mia_gemm_tn.restype = ci
+        L.mia_gemm.argtypes = [_vp, _vp, _vp, _vp, ci, ci, ci, ll, ll, ll, ci, ci, ci, ci, ci, _vp]
+        L.mia_gemm.restype = ci
         L.mia_gemm_last_error.restype = ctypes.c_char_p
         L.mia_ss_block_state_floats.argtypes = [ctypes.POINTER(MiaSSParams)]
         L.mia_ss_block_state_floats.restype = ctypes.c_size_t

@@ -200,6 +200,18 @@ __global__ void __launch_bounds__(kCsThreads) cross_merge_direct_kernel(const ty
     }
 }
 
+// out_z = out * silu(z): the gate of the mamba_ssm signature recomputed from the saved pre-gate output
+// (selective_scan_cuda.bwd(..., recompute_out_z=True), test_selective_scan.py:105-108); fp32 arithmetic, one rounding.
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256) silu_gate_kernel(const typename mia::Cvt<TO>::raw *__restrict__ out, const typename mia::Cvt<T>::raw *__restrict__ z,
+                                                        typename mia::Cvt<TO>::raw *__restrict__ out_z, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float zv = mia::Cvt<T>::to_f(z[i]);
+        const float y = mia::Cvt<TO>::to_f(out[i]);
+        out_z[i] = mia::Cvt<TO>::from_f(y * zv * mia::rcpf(1.f + mia::ex2f(-zv * mia::kLog2e)));
+    }
+}
+
 uint32_t cs_magic(int d) { return d == 1 ? 0u : (uint32_t)((0x100000000ULL + (uint64_t)d - 1) / (uint64_t)d); }
 
 thread_local char g_cs_err[256] = "";
@@ -292,4 +304,23 @@ int mia_cross_merge(const void *ys, void *y, int batch, int channels, int H, int
     return cs_dispatch(true, ys, y, batch, channels, H, W, dtype, cuda_stream);
 }
 const char *mia_cs_last_error(void) { return g_cs_err; }
+
+int mia_silu_gate(const void *out, const void *z, void *out_z, long long n, int z_dtype, int out_dtype, void *cuda_stream) {
+    if (!out || !z || !out_z) return cs_fail(MIA_EINVAL, "silu_gate: null pointer");
+    if (n <= 0) return cs_fail(MIA_EINVAL, "silu_gate: empty");
+    if (out_dtype != z_dtype && out_dtype != MIA_F32) return cs_fail(MIA_EINVAL, "silu_gate: out dtype must be z's dtype or float32");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    const int g = (int)blocks;
+#define MIA_GATE(T, TO) silu_gate_kernel<T, TO><<<g, 256, 0, st>>>((const typename mia::Cvt<TO>::raw *)out, (const typename mia::Cvt<T>::raw *)z, (typename mia::Cvt<TO>::raw *)out_z, n)
+    switch (z_dtype) {
+        case MIA_F32: MIA_GATE(float, float); break;
+        case MIA_F16: if (out_dtype == MIA_F32) MIA_GATE(__half, float); else MIA_GATE(__half, __half); break;
+        case MIA_BF16: if (out_dtype == MIA_F32) MIA_GATE(__nv_bfloat16, float); else MIA_GATE(__nv_bfloat16, __nv_bfloat16); break;
+        default: return cs_fail(MIA_EINVAL, "silu_gate: dtype must be MIA_F32, MIA_F16 or MIA_BF16");
+    }
+#undef MIA_GATE
+    return cs_cuda("silu_gate launch");
+}
 }

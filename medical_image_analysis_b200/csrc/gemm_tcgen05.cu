@@ -100,6 +100,14 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
            ((uint64_t)2 << 61);
 }
 
+// MN-major operand (the M / N index is the contiguous one, e.g. X^T or W^T read in place): TMA boxes of [64 k-rows x 64
+// mn-elements (128 bytes)] with the 128-byte swizzle, consecutive 64-wide mn slices 8192 bytes apart.  Canonical layout
+// ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) elements: LBO = 8192 B between mn slices, SBO = 1024 B between groups of 8 k-rows.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+
 __device__ __forceinline__ float act_apply(float v, int act) {
     switch (act) {
         case MIA_ACT_RELU: return fmaxf(v, 0.f);
@@ -111,7 +119,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 
 constexpr int kEpiSlab = 32 * 128;       // one epilogue staging slab: 32 rows x 128 bytes (one swizzle-128B TMA store box)
 
-template <int BN, int kStages>
+template <int BN, int kStages, bool kAMN, bool kBMN>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                   const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
     extern __shared__ char smem_raw[];
@@ -157,8 +165,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
                     mia::mbar_wait(empty + s, ph ^ 1);
                     mia::mbar_arrive_expect_tx(full + s, kStageBytes);
                     char *sa = tiles + s * kStageBytes, *sb = sa + kABytes;
-                    tma_load_2d(sa, &tmA, kb * kBK, mb * kBM, full + s);
-                    tma_load_2d(sb, &tmB, kb * kBK, nb * BN, full + s);
+                    if (kAMN) {
+#pragma unroll
+                        for (int i = 0; i < kBM / 64; ++i) tma_load_2d(sa + i * 8192, &tmA, mb * kBM + 64 * i, kb * kBK, full + s);
+                    } else {
+                        tma_load_2d(sa, &tmA, kb * kBK, mb * kBM, full + s);
+                    }
+                    if (kBMN) {
+#pragma unroll
+                        for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * 8192, &tmB, nb * BN + 64 * i, kb * kBK, full + s);
+                    } else {
+                        tma_load_2d(sb, &tmB, kb * kBK, nb * BN, full + s);
+                    }
                     if (++s == kStages) { s = 0; ph ^= 1; }
                 }
             }
@@ -168,7 +186,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
         if (lane == 0) {
             // instruction descriptor: D fp32, A / B bf16 (or fp16), both K-major, N = BN, M = 128
             const uint32_t fmt = g.in_f16 ? 0u : 1u;
-            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((kAMN ? 1u : 0u) << 15) | ((kBMN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
             int s = 0, as = 0;
             uint32_t ph = 0, aph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -179,10 +198,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_kernel(const __grid_c
                     mia::mbar_wait(full + s, ph);
                     tc_fence_after();
                     const uint32_t a_addr = mia::smem_u32(tiles + s * kStageBytes), b_addr = a_addr + kABytes;
-                    const uint64_t da = umma_desc_k_sw128(a_addr), db = umma_desc_k_sw128(b_addr);
+                    const uint64_t da = kAMN ? umma_desc_mn_sw128(a_addr) : umma_desc_k_sw128(a_addr);
+                    const uint64_t db = kBMN ? umma_desc_mn_sw128(b_addr) : umma_desc_k_sw128(b_addr);
+                    // 16 elements along K per instruction: K-major = 32 bytes inside the swizzle atom (+2 in the address field);
+                    // MN-major = 16 k-rows of 128 bytes = 2048 bytes (+128)
+                    constexpr uint64_t ka = kAMN ? 128 : 2, kbb = kBMN ? 128 : 2;
 #pragma unroll
-                    for (int k = 0; k < kBK / 16; ++k)      // 16 elements = 32 bytes along K inside the swizzle atom: +2 in the address field
-                        tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    for (int k = 0; k < kBK / 16; ++k)
+                        tc_mma_f16(tmem_d, da + ka * k, db + kbb * k, idesc, (kb | k) != 0);
                     tc_commit(empty + s);                   // the stage is free once these MMAs have read it
                     if (++s == kStages) { s = 0; ph ^= 1; }
                 }
@@ -345,6 +368,7 @@ EncodeTiledFn encode_fn() {
 // 2-D map of a row-major [rows][cols] matrix with row pitch ld (elements); box = [box_rows][128 bytes of columns], 128B swizzle.
 // dt: MIA_GEMM_F32 / F16 / BF16
 int make_map(CUtensorMap *tm, const void *ptr, long long rows, long long cols, long long ld, int box_rows, int dt) {
+    // rows x cols with cols contiguous; the box is [box_rows][128 bytes of columns]
     EncodeTiledFn fn = encode_fn();
     if (!fn) return gfail(MIA_GEMM_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
     const int es = dt == MIA_GEMM_F32 ? 4 : 2;
@@ -360,10 +384,10 @@ int make_map(CUtensorMap *tm, const void *ptr, long long rows, long long cols, l
     return MIA_GEMM_OK;
 }
 
-template <int BN, int kStages>
+template <int BN, int kStages, bool kAMN, bool kBMN>
 int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmC, GemmArgs &g, int sms, cudaStream_t stream) {
     constexpr int smem = kStages * (kBM * kBK * 2 + BN * kBK * 2) + 8 * kEpiSlab + (2 * kStages + 4) * 8 + 16 + 1024;
-    auto k = &gemm_tn_kernel<BN, kStages>;
+    auto k = &gemm_tn_kernel<BN, kStages, kAMN, kBMN>;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
         return gfail(MIA_GEMM_ECUDA, "cudaFuncSetAttribute(gemm, %d B): %s", smem, cudaGetErrorString(cudaGetLastError()));
     g.num_m_blocks = (g.M + kBM - 1) / kBM;
@@ -379,18 +403,15 @@ int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMa
 
 }  // namespace
 
-extern "C" {
-
-const char *mia_gemm_last_error(void) { return g_gemm_err; }
-
-int mia_gemm_tn(const void *A, const void *W, const float *bias, void *C, int M, int N, int K, long long lda, long long ldw, long long ldc,
-                int in_dtype, int out_dtype, int act, void *cuda_stream) {
+static int gemm_impl(const void *A, const void *W, const float *bias, void *C, int M, int N, int K, long long lda, long long ldw, long long ldc,
+                     int a_mn, int b_mn, int in_dtype, int out_dtype, int act, void *cuda_stream) {
     if (!A || !W || !C) return gfail(MIA_GEMM_EINVAL, "gemm: null pointer");
     if (M <= 0 || N <= 0 || K <= 0) return gfail(MIA_GEMM_EINVAL, "gemm: empty or negative size (M %d, N %d, K %d)", M, N, K);
     if (in_dtype != MIA_GEMM_BF16 && in_dtype != MIA_GEMM_F16) return gfail(MIA_GEMM_EINVAL, "gemm: inputs must be bf16 or fp16");
     if (out_dtype != in_dtype && out_dtype != MIA_GEMM_F32) return gfail(MIA_GEMM_EINVAL, "gemm: output must be the input dtype or fp32");
     if (act < 0 || act > MIA_ACT_SILU) return gfail(MIA_GEMM_EINVAL, "gemm: unknown activation %d", act);
-    if ((lda % 8) || (ldw % 8) || lda < K || ldw < K) return gfail(MIA_GEMM_EINVAL, "gemm: row pitches must be >= K and multiples of 8 elements (lda %lld, ldw %lld, K %d)", lda, ldw, K);
+    if ((lda % 8) || (ldw % 8) || lda < (a_mn ? M : K) || ldw < (b_mn ? N : K))
+        return gfail(MIA_GEMM_EINVAL, "gemm: row pitches must cover a row and be multiples of 8 elements (lda %lld, ldw %lld, M %d, N %d, K %d)", lda, ldw, M, N, K);
     if (((uintptr_t)A | (uintptr_t)W) & 15) return gfail(MIA_GEMM_EINVAL, "gemm: A and W must be 16-byte aligned");
     if (ldc < N) return gfail(MIA_GEMM_EINVAL, "gemm: ldc < N");
     int dev = 0, sms = 0;
@@ -402,8 +423,9 @@ int mia_gemm_tn(const void *A, const void *W, const float *bias, void *C, int M,
     g.in_f16 = in_dtype == MIA_GEMM_F16; g.C = C; g.ldc = ldc;
     const int BN = N <= 64 ? 64 : (N <= 128 || (long long)((M + 127) / 128) * ((N + 255) / 256) < sms ? 128 : 256);
     CUtensorMap tmA, tmB, tmC;
-    if (int rc = make_map(&tmA, A, M, K, lda, kBM, in_dtype)) return rc;
-    if (int rc = make_map(&tmB, W, N, K, ldw, BN, in_dtype)) return rc;
+    // K-major operand: [rows = M or N][cols = K], box [tile rows][64 k];  MN-major operand: stored [rows = K][cols = M or N], box [64 k][64 mn]
+    if (int rc = a_mn ? make_map(&tmA, A, K, M, lda, kBK, in_dtype) : make_map(&tmA, A, M, K, lda, kBM, in_dtype)) return rc;
+    if (int rc = b_mn ? make_map(&tmB, W, K, N, ldw, kBK, in_dtype) : make_map(&tmB, W, N, K, ldw, BN, in_dtype)) return rc;
     const int eo = g.out_f32 ? 4 : 2;
     g.tma_store = (((uintptr_t)C & 15) == 0) && ((ldc * eo) % 16 == 0);
     if (g.tma_store) {
@@ -412,11 +434,31 @@ int mia_gemm_tn(const void *A, const void *W, const float *bias, void *C, int M,
         tmC = tmA;                                   // unused by the kernel on the direct-store path
     }
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    switch (BN) {
-        case 64: return launch_gemm<64, 8>(tmA, tmB, tmC, g, sms, stream);
-        case 128: return launch_gemm<128, 6>(tmA, tmB, tmC, g, sms, stream);
-        default: return launch_gemm<256, 4>(tmA, tmB, tmC, g, sms, stream);
+#define MIA_GEMM_LAUNCH(AMN, BMN)                                                          \
+    switch (BN) {                                                                          \
+        case 64: return launch_gemm<64, 8, AMN, BMN>(tmA, tmB, tmC, g, sms, stream);       \
+        case 128: return launch_gemm<128, 6, AMN, BMN>(tmA, tmB, tmC, g, sms, stream);     \
+        default: return launch_gemm<256, 4, AMN, BMN>(tmA, tmB, tmC, g, sms, stream);      \
     }
+    if (!a_mn && !b_mn) { MIA_GEMM_LAUNCH(false, false) }
+    if (!a_mn && b_mn) { MIA_GEMM_LAUNCH(false, true) }
+    if (a_mn && b_mn) { MIA_GEMM_LAUNCH(true, true) }
+    MIA_GEMM_LAUNCH(true, false)
+#undef MIA_GEMM_LAUNCH
+}
+
+extern "C" {
+
+const char *mia_gemm_last_error(void) { return g_gemm_err; }
+
+int mia_gemm_tn(const void *A, const void *W, const float *bias, void *C, int M, int N, int K, long long lda, long long ldw, long long ldc,
+                int in_dtype, int out_dtype, int act, void *cuda_stream) {
+    return gemm_impl(A, W, bias, C, M, N, K, lda, ldw, ldc, 0, 0, in_dtype, out_dtype, act, cuda_stream);
+}
+
+int mia_gemm(const void *A, const void *B, const float *bias, void *C, int M, int N, int K, long long lda, long long ldb, long long ldc,
+             int a_mn_major, int b_mn_major, int in_dtype, int out_dtype, int act, void *cuda_stream) {
+    return gemm_impl(A, B, bias, C, M, N, K, lda, ldb, ldc, a_mn_major != 0, b_mn_major != 0, in_dtype, out_dtype, act, cuda_stream);
 }
 
 }  // extern "C"

@@ -478,6 +478,10 @@ bool plan_win_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::WinBwdArgs 
     const int rpg = p.dim / p.n_groups;
     if (!p.hblk || p.dstate != 1 || p.z || p.delta_dim != p.dim || (rpg % 32) || (L % 4)) return false;
     if (dbg_knob("MIA_NO_WIN_BWD")) return false;
+    // Measured on B200 (gpurun r2e): L = 6400, B = 16: 1.17 ms vs 1.78 ms for the warp-scan kernel (and no per-CTA residency
+    // condition); L = 196, B = 148: 0.43 ms vs 0.37 ms for the resident-row kernel (7 windows of which the last holds 4
+    // tokens, 8-byte cp.async pieces) -> rows of more than one 256-token chunk only, unless forced for the tests.
+    if (L <= mia::kRowsChunk && !dbg_knob("MIA_FORCE_WIN_BWD")) return false;
     auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
     if (!dense(p.u_batch_stride, p.u_d_stride) || !dense(p.delta_batch_stride, p.delta_d_stride) ||
         !dense(p.dout_batch_stride, p.dout_d_stride) || !dense(p.du_batch_stride, p.du_d_stride) ||
@@ -491,8 +495,10 @@ bool plan_win_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::WinBwdArgs 
     r.n_items = p.batch * p.n_groups * (rpg / 32);
     r.nblk = (L + mia::kBlk - 1) / mia::kBlk;
     r.nwin = (L + mia::kWinTok - 1) / mia::kWinTok;
-    r.pitch = mia::kWinTok * es + 8;
-    r.pitcho = mia::kWinTok * eo + 8;
+    // +8 bytes (2-byte types: rows stay 8-byte aligned for the 4-token quads) / +16 (fp32: 16-byte quads): shifts the rows
+    // across the shared-memory banks
+    r.pitch = mia::kWinTok * es + (es == 4 ? 16 : 8);
+    r.pitcho = mia::kWinTok * eo + (eo == 4 ? 16 : 8);
     r.off_u = 0;
     r.off_d = round_up(32 * r.pitch, 16);
     r.off_o = 2 * r.off_d;

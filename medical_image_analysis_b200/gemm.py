@@ -5,8 +5,8 @@
 calls cuBLAS through ``nn.Linear`` / ``torch.einsum`` (vmamba.py:386, 751, 775; mamba_simple.py:408-414, 686-689, 708;
 mae.py:64-66, 82-84) or cuDNN through kernel==stride convolutions (patch_embed.py:25-29).
 
-Backward: dX = dY . W and dW = dY^T . X run on the same kernel (it contracts over the contiguous dimension of both
-operands, so the operands that are not laid out that way are transposed first by ``transpose2d``); dbias is a column sum.
+Backward: dX = dY . W and dW = dY^T . X run on the same kernel with MN-major operand descriptors (``gemm(..., a_mn, b_mn)``:
+the transposed operand is read in place, no copies); dbias is a column sum.
 fp32 activations (no autocast) are NOT silently rounded to bf16: they take ``F.linear`` like in the reference.
 """
 from __future__ import annotations
@@ -58,6 +58,34 @@ def gemm_tn(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, 
     return c
 
 
+def gemm(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool = False, out_dtype=None) -> torch.Tensor:
+    """General tcgen05 contraction without copies: ``C[M, N] = sum_k A(m, k) B(n, k)`` where each operand is either stored
+    [rows = M or N][K] (``*_mn=False``) or [K][M or N] (``*_mn=True``: its transpose read in place, MN-major UMMA operand).
+    Both must be bf16 / fp16, last dim contiguous, pitches multiples of 8 elements, 16-byte aligned."""
+    K = a.shape[0] if a_mn else a.shape[1]
+    M = a.shape[1] if a_mn else a.shape[0]
+    N = b.shape[1] if b_mn else b.shape[0]
+    if (b.shape[0] if b_mn else b.shape[1]) != K:
+        raise RuntimeError(f"gemm: operands {tuple(a.shape)} (mn={a_mn}) and {tuple(b.shape)} (mn={b_mn}) do not contract")
+    for t in (a, b):
+        if t.dtype not in (torch.bfloat16, torch.float16) or t.dtype != a.dtype or not t.is_cuda:
+            raise RuntimeError("gemm: bf16 / fp16 CUDA operands of one dtype required")
+        if t.stride(1) != 1 or t.stride(0) % 8 or t.data_ptr() % 16:
+            raise RuntimeError("gemm: operands need a contiguous last dim, a row pitch that is a multiple of 8 and 16-byte alignment")
+    out_dtype = out_dtype or a.dtype
+    c = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = _lib.lib().mia_gemm(a.data_ptr(), b.data_ptr(), None, c.data_ptr(), M, N, K, a.stride(0), b.stride(0), c.stride(0), int(a_mn),
+                                 int(b_mn), _DT[a.dtype], _DT[out_dtype], ACT_NONE, _stream(a))
+    if rc != 0:
+        raise RuntimeError(f"mia_gemm: {_lib.lib().mia_gemm_last_error().decode()} (code {rc})")
+    return c
+
+
+def _mn_ok(t: torch.Tensor) -> bool:
+    return t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0
+
+
 def transpose2d(t: torch.Tensor) -> torch.Tensor:
     """(R, C) -> contiguous (C, R)."""
     return t.t().contiguous()
@@ -94,10 +122,12 @@ class LinearTC(torch.autograd.Function):
             raise NotImplementedError("fused SiLU epilogue is inference-only")
         dy = dy.contiguous()
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = gemm_tn(dy, transpose2d(w))                     # (M, N) x (K, N)^T
-        if ctx.needs_input_grad[1]:
-            dw = gemm_tn(transpose2d(dy), transpose2d(x), out_dtype=torch.float32).to(ctx.wdtype)   # (N, M) x (K, M)^T
+        direct = _mn_ok(dy) and _mn_ok(w) and _mn_ok(x)         # MN-major operands read in place (no transposed copies)
+        if ctx.needs_input_grad[0]:                               # dX[tok, in] = dY[tok, out] . W[out, in]
+            dx = gemm(dy, w, False, True) if direct else gemm_tn(dy, transpose2d(w))
+        if ctx.needs_input_grad[1]:                               # dW[out, in] = dY[tok, out]^T . X[tok, in]
+            dw = (gemm(dy, x, True, True, torch.float32) if direct
+                  else gemm_tn(transpose2d(dy), transpose2d(x), out_dtype=torch.float32)).to(ctx.wdtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.float().sum(0).to(ctx.bdtype)
         return dx, dw, db, None, None

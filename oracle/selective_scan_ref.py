@@ -99,3 +99,39 @@ def selective_scan_ref_fwd_bwd(u, delta, A, B, C, D, z, delta_bias, delta_softpl
     g = lambda t: None if t is None else t.grad
     return dict(out=out.detach(), last_state=last.detach(), du=g(u_), ddelta=g(d_small),
                 dA=g(A_), dB=g(B_), dC=g(C_), dD=g(D_), dz=g(z_), ddelta_bias=g(b_small))
+
+
+def selective_scan_ref_v2(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, return_last_state=False):
+    """Follows test_selective_scan.py:237-306: the low-precision behaviour model -- every operand is first cast to u's
+    dtype (:253-259) and the whole recurrence runs in that dtype (real A, variable B / C of rank 3 or 4).  Not a parity
+    target of the kernels (they compute in fp32 like selective_scan_ref); restated so that the reference's second oracle
+    has a counterpart, pinned to vectors of the reference's own function (tests/golden/scan_ref_v2.npz)."""
+    dt_in = u.dtype
+    A, B, C = A.to(dt_in), B.to(dt_in), C.to(dt_in)
+    D = None if D is None else D.to(dt_in)
+    z = None if z is None else z.to(dt_in)
+    delta = delta.to(dt_in)
+    if delta_bias is not None:
+        delta = delta + delta_bias.to(dt_in)[..., None]
+    if delta_softplus:
+        delta = F.softplus(delta)
+    batch, dim, N = u.shape[0], A.shape[0], A.shape[1]
+    dA = torch.exp(torch.einsum("bdl,dn->bdln", delta, A))
+    if B.dim() == 3:
+        dBu = torch.einsum("bdl,bnl,bdl->bdln", delta, B, u)
+    else:
+        dBu = torch.einsum("bdl,bdnl,bdl->bdln", delta, B.repeat_interleave(dim // B.shape[1], dim=1), u)
+    if C.dim() == 4:
+        C = C.repeat_interleave(dim // C.shape[1], dim=1)
+    h = A.new_zeros((batch, dim, N))
+    ys = []
+    for i in range(u.shape[2]):
+        h = dA[:, :, i] * h + dBu[:, :, i]
+        ys.append(torch.einsum("bdn,bn->bd", h, C[:, :, i]) if C.dim() == 3 else torch.einsum("bdn,bdn->bd", h, C[:, :, :, i]))
+    out = torch.stack(ys, dim=2)
+    if D is not None:
+        out = out + u * D.unsqueeze(-1)
+    if z is not None:
+        out = out * F.silu(z)
+    out = out.to(dt_in)
+    return (out, h.float()) if return_last_state else out

@@ -145,5 +145,28 @@ def main():
     print("cross_scan done")
 
 
+
+
+def make_ref_v2():
+    """selective_scan_ref_v2 (test_selective_scan.py:237-306): vectors for oracle/selective_scan_ref.py::selective_scan_ref_v2."""
+    (v2,) = lift(f"{REF}/R2GenCSR/VMamba/kernels/selective_scan/test_selective_scan.py", ["selective_scan_ref_v2"])
+    store, specs, k = {}, [], 0
+    for dtype in (torch.float32, torch.bfloat16):
+        for (N, G, L, has_z) in ((1, 1, 24, False), (4, 2, 19, True), (16, 1, 17, False)):
+            inp = make_inputs(2000 + k, 2, 4, L, N, G, 4, True, has_z, True, dtype)
+            out, last = v2(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["z"], inp["delta_bias"], True, True)
+            tag = f"v{k}"
+            specs.append(f"{tag}|{N}|{G}|{L}|{int(has_z)}|{'bf16' if dtype == torch.bfloat16 else 'f32'}")
+            for n, t in inp.items():
+                if t is not None and n != "dout":
+                    store[f"{tag}.in.{n}"] = to_np(t)
+            store[f"{tag}.out"], store[f"{tag}.last"] = to_np(out), to_np(last)
+            k += 1
+    store["specs"] = np.array(specs)
+    np.savez_compressed(os.path.join(HERE, "scan_ref_v2.npz"), **store)
+    print("scan_ref_v2:", k, "cases")
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    main()
+    make_ref_v2()

@@ -88,3 +88,24 @@ def test_linear_autograd_matches_torch(act):
         cmp_stored(xg.grad, xr.grad, torch.bfloat16, f"linear act{act} dx", n_ulp=2.0)      # dy rounded again after the activation derivative
         cmp_stored(wg.grad, wr.grad, torch.bfloat16, f"linear act{act} dw", n_ulp=2.0)
     assert torch.allclose(bg.grad.double().cpu(), br.grad, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 64), (200, 136, 72), (392, 80, 768), (61, 3072, 1024), (1000, 56, 264), (64, 256, 4096)],
+                         ids=lambda s: f"M{s[0]}N{s[1]}K{s[2]}")
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, True), (True, False)])
+def test_gemm_mn_major_operands(shape, a_mn, b_mn):
+    """Operands read in place with their M / N index contiguous (UMMA a_major / b_major = MN): what the backward of a linear
+    layer contracts, checked against fp64 on the same bf16 values."""
+    from medical_image_analysis_b200.gemm import gemm
+    from tests.parity import cmp_f32
+    M, N, K = shape
+    if (a_mn and M % 8) or (b_mn and N % 8):
+        pytest.skip("MN-major operands need a 16-byte row pitch")
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
+    a = (torch.randn(M, K, generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, K, generator=g).bfloat16()
+    ref = a.double() @ b.double().t()
+    a_dev = a.t().contiguous().cuda() if a_mn else a.cuda()           # stored [K][M] when MN-major
+    b_dev = b.t().contiguous().cuda() if b_mn else b.cuda()
+    out = gemm(a_dev, b_dev, a_mn, b_mn, torch.float32)
+    cmp_f32(out, ref, f"gemm mn a{int(a_mn)} b{int(b_mn)} M{M} N{N} K{K}", rtol=1e-4, atol_rms=1e-4)

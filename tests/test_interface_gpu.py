@@ -174,3 +174,20 @@ def test_bimamba_inner_fn_is_two_directions():
     assert tuple(out.shape) == (b, L, 5) and torch.isfinite(out).all()
     fwd_only = F.linear(mamba_inner_fn_no_out_proj(xz, cw, cb, xp, dp, A, None, None, D, delta_bias=bias).transpose(1, 2), ow)
     assert not torch.allclose(out, fwd_only)
+
+
+def test_selective_scan_cuda_bwd_recompute_out_z_is_a_kernel():
+    """selective_scan_cuda.bwd(..., recompute_out_z=True) returns out * silu(z) (mia_silu_gate), equal to the forward's out_z."""
+    from medical_image_analysis_b200 import selective_scan_cuda as ssc
+    g = torch.Generator().manual_seed(4)
+    u = torch.randn(2, 32, 40, generator=g).bfloat16().cuda()
+    delta = (0.5 * torch.rand(2, 32, 40, generator=g)).bfloat16().cuda()
+    A = (-0.5 * torch.rand(32, 4, generator=g)).cuda()
+    B = torch.randn(2, 4, 40, generator=g).bfloat16().cuda()
+    C = torch.randn(2, 4, 40, generator=g).bfloat16().cuda()
+    z = torch.randn(2, 32, 40, generator=g).bfloat16().cuda()
+    out, x, out_z = ssc.fwd(u, delta, A, B, C, None, z, None, True)
+    res = ssc.bwd(u, delta, A, B, C, None, z, None, torch.randn_like(out), x, out, None, True, True)
+    assert len(res) == 9
+    ref = (out.float() * torch.nn.functional.silu(z.float())).to(out.dtype)
+    assert torch.allclose(res[-1].float(), ref.float(), rtol=1e-2, atol=1e-2)

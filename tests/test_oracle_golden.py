@@ -67,3 +67,21 @@ def test_c1_config_against_reference():
     got = port.selective_scan_ref(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], None,
                                   inp["delta_bias"], True)
     _close(got, ref["out"], 1e-5, 1e-5, "port out")
+
+
+def test_oracle_ref_v2_matches_reference_vectors():
+    """oracle.selective_scan_ref_v2 vs the reference's selective_scan_ref_v2 (test_selective_scan.py:237-306), same dtype arithmetic."""
+    import os
+    import numpy as np
+    from oracle.selective_scan_ref import selective_scan_ref_v2
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scan_ref_v2.npz"))
+    for spec in z["specs"]:
+        tag, N, G, L, has_z, dt = str(spec).split("|")
+        dtype = torch.bfloat16 if dt == "bf16" else torch.float32
+        get = lambda n, cast=True: (torch.from_numpy(z[f"{tag}.in.{n}"]).to(dtype) if cast else torch.from_numpy(z[f"{tag}.in.{n}"]))
+        zz = get("z") if f"{tag}.in.z" in z.files else None
+        out, last = selective_scan_ref_v2(get("u"), get("delta"), get("A", False), get("B"), get("C"), get("D", False), zz,
+                                          get("delta_bias", False), True, True)
+        tol = 1e-6 if dt == "f32" else 2e-2
+        assert torch.allclose(out.float(), torch.from_numpy(z[f"{tag}.out"]), rtol=tol, atol=tol), tag
+        assert torch.allclose(last, torch.from_numpy(z[f"{tag}.last"]), rtol=tol, atol=tol), tag
