@@ -12,18 +12,23 @@
 #include "scan_bwd_rows.cuh"
 #include "scan_bwd_rowsn.cuh"
 #include "scan_bwd_win.cuh"
+#include "scan_bwd_wtma.cuh"
+#include "tma_host.h"
 #include "scan_fwd_rowsn.cuh"
 #include "scan_fwd_stream.cuh"
 #include "scan_fwd_chunks.cuh"
+#include "scan_fwd_cw.cuh"
 
 namespace mia {
 template <typename T> cudaError_t launch_fwd_rows(const RowsArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_fwd_rowsn(const RowsNArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_fwd_stream(const StreamArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_fwd_chunks(const ChunkArgs &, int, bool, cudaStream_t);
+template <typename T> cudaError_t launch_fwd_cw(const CUtensorMap *, const CwFwdArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_rows(const RowsBwdArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_rowsn(const RowsNBwdArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_win(const WinBwdArgs &, int, bool, cudaStream_t);
+template <typename T> cudaError_t launch_bwd_wtma(const CUtensorMap *, const WinTmaArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_fwd_any(const ScanArgs &, int, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_any(const ScanArgs &, int, cudaStream_t);
 }  // namespace mia
@@ -51,7 +56,9 @@ int fail(int code, const char *fmt, ...) {
 #ifdef MIA_DEBUG
 bool dbg_knob(const char *name) { return getenv(name) != nullptr; }
 int dbg_int(const char *name, int dflt) { const char *v = getenv(name); return v ? atoi(v) : dflt; }
+#define MIA_TRACE(...) do { if (getenv("MIA_TRACE")) { fprintf(stderr, "[mia] " __VA_ARGS__); fputc('\n', stderr); } } while (0)
 #else
+#define MIA_TRACE(...) do { } while (0)
 constexpr bool dbg_knob(const char *) { return false; }
 constexpr int dbg_int(const char *, int dflt) { return dflt; }
 #endif
@@ -282,6 +289,19 @@ int plan_and_layout(const mia_ss_params &p, const DeviceInfo &di, bool bwd, Plan
     }
 }
 
+// Geometry of the column-walk kernels (scan_fwd_cw.cuh / scan_bwd_cw.cuh): g rows per tensor-map row.  A pure function of the
+// problem's sizes and dtypes -- it also fixes the LAYOUT of the block states (hblk), which forward and backward must agree on:
+// for g == 2 only the column-walk kernels may write / read them.
+bool cw_geometry(const mia_ss_params &p, int &g) {
+    const int es = esize(p.itype), L = p.seqlen;
+    if (p.dstate != 1 || p.z || p.delta_dim != p.dim || (L % 4) || p.n_groups < 1) return false;
+    const int rpg = p.dim / p.n_groups;
+    if (((long long)L * es) % 16 == 0) g = 1;
+    else if (es == 2) g = 2;                                     // L % 8 == 4: two rows make a 16-byte multiple
+    else return false;
+    return rpg % (32 * g) == 0;
+}
+
 // Row-serial forward (scan_fwd_rows.cuh): eligibility + argument block.  Returns false when the warp-scan kernels must run.
 bool plan_rows_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsArgs &r, int &grid) {
     const int es = esize(p.itype), L = p.seqlen;
@@ -312,10 +332,77 @@ bool plan_rows_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsArgs &
     r.xchunks = mia_ss_num_chunks(L); r.xchunk_tokens = mia_ss_chunk_len(L);
     r.u = p.u; r.delta = p.delta; r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.out = p.out; r.x = p.x;
     r.hblk = p.hblk; r.nblk16 = (L + 15) / 16;
+    {
+        int g = 0;
+        if (cw_geometry(p, g) && g == 2) r.hblk = nullptr;      // block states of such shapes have the column-walk layout: not ours to write
+    }
     r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride;
     const int per_sm = di.smem_optin / (r.smem_bytes + 1024) > 0 ? (227 * 1024) / (r.smem_bytes + 1024) : 1;
     grid = di.sms * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
     if (grid > r.n_items) grid = r.n_items;
+    return true;
+}
+
+// Column-walk forward (scan_fwd_cw.cuh): eligibility, argument block, tensor maps (u, delta, out).
+bool plan_cw_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::CwFwdArgs &r, CUtensorMap *tm, int &grid) {
+    const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
+    int g = 0;
+    if (!cw_geometry(p, g)) return false;
+    if (dbg_knob("MIA_NO_CW_FWD")) return false;
+    const int rpg = p.dim / p.n_groups;
+    auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
+    if (!dense(p.u_batch_stride, p.u_d_stride) || !dense(p.delta_batch_stride, p.delta_d_stride) ||
+        !dense(p.out_batch_stride, p.out_d_stride)) return false;
+    if (p.A_d_stride != 1 && p.dim > 1) return false;
+    if (((uintptr_t)p.u | (uintptr_t)p.delta | (uintptr_t)p.out) & 15) return false;
+    const unsigned long long trows = (unsigned long long)p.batch * p.dim / g, tcols = (unsigned long long)g * L;
+    if (tcols >= (1ull << 31) || trows >= (1ull << 31)) return false;
+    const int n_items = p.batch * p.n_groups * (rpg / (32 * g));
+    // few long rows: the chunk-parallel kernel (scan_fwd_chunks.cuh) has more warps to offer than one per 32 rows
+    if (n_items < 4 * di.sms && (L + mia::kChunkTok - 1) / mia::kChunkTok >= 2 && !dbg_knob("MIA_FORCE_CW_FWD")) return false;
+    memset(&r, 0, sizeof(r));
+    r.batch = p.batch; r.dim = p.dim; r.L = L; r.G = p.n_groups; r.rows_per_group = rpg; r.softplus = p.delta_softplus;
+    r.g = g; r.n_items = n_items;
+    r.nwin = (g * L + mia::kCwTok - 1) / mia::kCwTok;
+    r.ngrp = (g * L + 15) / 16;
+    const bool of32 = eo == 4 && es != 4;
+    const int tile_i = 32 * mia::kCwTok * es, tile_o = 32 * mia::kCwTok * eo;
+    r.stage_bytes = 2 * tile_i;
+    // stages: 4 unless 3 gives a better-balanced last round (more resident warps)
+    int best_ns = 0, best_per_sm = 0;
+    double best_eff = -1.0;
+    for (int ns = 4; ns >= 3; --ns) {
+        const int smem = ns * r.stage_bytes + (of32 ? 2 * tile_o : 0) + 2 * mia::kCwTok * 4 + 8 * ns + 16 + 1024;
+        int per_sm = (227 * 1024) / (smem + 1024);
+        if (per_sm > 16) per_sm = 16;
+        if (per_sm < 1) continue;
+        const long long slots = (long long)di.sms * per_sm;
+        const long long rounds = (n_items + slots - 1) / slots;
+        const double eff = (double)n_items / (double)(rounds * slots) * (per_sm >= 8 ? 1.0 : per_sm / 8.0);
+        if (eff > best_eff + 0.03) { best_eff = eff; best_ns = ns; best_per_sm = per_sm; }
+    }
+    if (!best_ns) return false;
+    r.ns = dbg_int("MIA_CW_STAGES", best_ns);
+    r.off_out = r.ns * r.stage_bytes;
+    r.off_bc32 = r.off_out + (of32 ? 2 * tile_o : 0);
+    r.off_bar = r.off_bc32 + 2 * mia::kCwTok * 4;
+    r.smem_bytes = r.off_bar + 8 * r.ns + 16 + 1024;            // + slack for the 1024-byte alignment of the tiles
+    r.xchunks = mia_ss_num_chunks(L); r.xchunk_tokens = mia_ss_chunk_len(L);
+    r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.x = p.x; r.hblk = p.hblk;
+    r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride;
+    const void *ptrs[3] = {p.u, p.delta, p.out};
+    for (int i = 0; i < 3; ++i) {
+        const int e = i == 2 ? eo : es;
+        const int trc = mia::tma_make_2d(&tm[i], ptrs[i], trows, tcols, tcols * e, 32, mia::kCwTok, e, mia::kCwTok * e);
+        if (trc != 0) { MIA_TRACE("cw fwd: tensor map %d rejected (CUresult %d)", i, trc); return false; }
+    }
+    int per_sm = (227 * 1024) / (r.smem_bytes + 1024);
+    if (per_sm > 16) per_sm = 16;
+    if (per_sm < 1) return false;
+    const long long slots = (long long)di.sms * per_sm;
+    const long long rounds = (n_items + slots - 1) / slots;
+    grid = (int)((n_items + rounds - 1) / rounds);              // equal rounds per CTA
+    (void)best_per_sm;
     return true;
 }
 
@@ -517,6 +604,54 @@ bool plan_win_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::WinBwdArgs 
     return true;
 }
 
+// Windowed row-serial backward fed by tensor-map TMA boxes (scan_bwd_wtma.cuh): eligibility, argument block, the five tensor maps
+// (u, delta, dout, du, ddelta).  Rows whose byte pitch is not a multiple of 16 are mapped two to a tensor-map row (g = 2).
+bool plan_wtma_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::WinTmaArgs &r, CUtensorMap *tm, int &grid) {
+    const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
+    const int rpg = p.dim / p.n_groups;
+    if (!p.hblk || p.dstate != 1 || p.z || p.delta_dim != p.dim || (rpg % 32) || (L % 4)) return false;
+    if (dbg_knob("MIA_NO_WTMA_BWD")) return false;
+    auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
+    if (!dense(p.u_batch_stride, p.u_d_stride) || !dense(p.delta_batch_stride, p.delta_d_stride) ||
+        !dense(p.dout_batch_stride, p.dout_d_stride) || !dense(p.du_batch_stride, p.du_d_stride) ||
+        !dense(p.ddelta_batch_stride, p.ddelta_d_stride)) return false;
+    if (p.A_d_stride != 1 && p.dim > 1) return false;
+    if (((uintptr_t)p.u | (uintptr_t)p.delta | (uintptr_t)p.dout | (uintptr_t)p.du | (uintptr_t)p.ddelta) & 15) return false;
+    if (((long long)L * es) % 16) return false;                  // rows must be tensor-map rows (else: the column-walk kernels)
+    const int g = 1;
+    const unsigned long long trows = (unsigned long long)p.batch * p.dim / g, tcols = (unsigned long long)g * L;
+    if (tcols >= (1ull << 31) || trows >= (1ull << 31)) return false;
+    memset(&r, 0, sizeof(r));
+    r.batch = p.batch; r.dim = p.dim; r.L = L; r.G = p.n_groups; r.rows_per_group = rpg; r.softplus = p.delta_softplus;
+    r.n_items = p.batch * p.n_groups * (rpg / 32);
+    r.nblk = (L + mia::kBlk - 1) / mia::kBlk;
+    r.nwin = (L + mia::kWtTok - 1) / mia::kWtTok;
+    r.g = g;
+    const int tile_i = 32 * mia::kWtTok * es, tile_o = 32 * mia::kWtTok * eo;
+    r.off_d = tile_i; r.off_o = 2 * tile_i;
+    r.in_stage = 2 * tile_i + tile_o;
+    r.out_stage = 2 * tile_i;
+    r.off_outs = 2 * r.in_stage;
+    r.off_bc32 = r.off_outs + r.out_stage;
+    r.off_bar = r.off_bc32 + 2 * mia::kWtTok * 4;
+    r.smem_bytes = r.off_bar + 16 + 1024;                        // + slack for the 1024-byte alignment of the tiles
+    r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias;
+    r.hblk = p.hblk; r.du = p.du; r.ddelta = p.ddelta;
+    r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride;
+    const void *ptrs[5] = {p.u, p.delta, p.dout, p.du, p.ddelta};
+    for (int i = 0; i < 5; ++i) {
+        const int e = i == 2 ? eo : es;
+        const int trc = mia::tma_make_2d(&tm[i], ptrs[i], trows, tcols, tcols * e, 32 / g, mia::kWtTok, e, mia::kWtTok * e);
+        if (trc != 0) { MIA_TRACE("wtma: tensor map %d rejected (CUresult %d): rows %llu cols %llu", i, trc, trows, tcols); return false; }
+    }
+    int per_sm = (227 * 1024) / (r.smem_bytes + 1024);
+    if (per_sm > 12) per_sm = 12;                               // 32 threads x 168 registers: 3 warps per scheduler
+    if (per_sm < 1) return false;
+    grid = di.sms * per_sm;
+    if (grid > r.n_items) grid = r.n_items;
+    return true;
+}
+
 // Deterministic d_state 16 backward (scan_bwd_rowsn.cuh): eligibility + argument block.
 bool plan_rowsn_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsNBwdArgs &r, int &grid) {
     const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
@@ -700,8 +835,12 @@ int mia_ss_fwd_writes_block_states(const mia_ss_params *pp) {
     if (device_info(di) != MIA_OK) return 0;
     mia::ChunkArgs rc;
     mia::RowsArgs rr;
-    int grid = 0;
-    return (plan_chunks_fwd(*pp, di, rc, grid) || plan_rows_fwd(*pp, di, rr, grid)) ? 1 : 0;   // the two kernels that fill hblk
+    mia::CwFwdArgs rw;
+    CUtensorMap tm[3];
+    int grid = 0, g = 0;
+    if (plan_cw_fwd(*pp, di, rw, tm, grid)) return 1;
+    if (cw_geometry(*pp, g) && g == 2) return 0;                 // that layout is the column-walk kernels' alone
+    return (plan_chunks_fwd(*pp, di, rc, grid) || plan_rows_fwd(*pp, di, rr, grid)) ? 1 : 0;   // the other two kernels that fill hblk
 }
 
 int mia_selective_scan_fwd(const mia_ss_params *pp, void *cuda_stream) {
@@ -713,6 +852,22 @@ int mia_selective_scan_fwd(const mia_ss_params *pp, void *cuda_stream) {
     DeviceInfo di;
     if (int rc = device_info(di)) return rc;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
+    {
+        mia::CwFwdArgs r;
+        CUtensorMap tm[3];
+        int rgrid = 0;
+        if (plan_cw_fwd(p, di, r, tm, rgrid)) {
+            MIA_TRACE("fwd: cw g=%d ns=%d nwin=%d grid=%d smem=%d", r.g, r.ns, r.nwin, rgrid, r.smem_bytes);
+            const bool of32 = p.otype == MIA_F32 && p.itype != MIA_F32;
+            const int rc = dispatch(p.itype, [&](auto *tag) {
+                using T = typename std::remove_pointer<decltype(tag)>::type;
+                return (int)mia::launch_fwd_cw<T>(tm, r, rgrid, of32, stream);
+            });
+            if (rc != 0) return fail(MIA_ECUDA, "selective_scan_fwd (column-walk) launch: %s", cudaGetErrorString((cudaError_t)rc));
+            g_launches.fetch_add(1);
+            return MIA_OK;
+        }
+    }
     {
         mia::ChunkArgs r;
         int rgrid = 0;
@@ -837,7 +992,27 @@ int mia_selective_scan_bwd(const mia_ss_params *pp, void *cuda_stream) {
     mia::RowsBwdArgs rb;
     mia::WinBwdArgs wb;
     int rgrid = 0;
-    if (!use_rowsn && plan_win_bwd(p, di, wb, rgrid)) {
+    mia::WinTmaArgs wt;
+    CUtensorMap tmaps[5];
+    int cwg = 0;
+    const bool hblk_std = p.hblk && !(cw_geometry(p, cwg) && cwg == 2);      // block states in the token-aligned layout
+    // Windowed kernels (one warp per 32 rows, phase 2 only): rows of more than one 256-token chunk, and enough 32-row items to
+    // fill the SMs.  Measured (gpurun r2i, L = 6400, bf16): B = 16 (1536 items) 1.16 ms against 1.76 ms for the warp-scan
+    // kernel; B = 4 (384 items = 2.6 warps per SM) 0.75 ms against 0.55 ms.
+    const long long items32 = (long long)p.batch * (p.dim / 32);
+    const bool want_win = !use_rowsn && hblk_std &&
+                          ((p.seqlen > mia::kRowsChunk && items32 >= 4LL * di.sms) || dbg_knob("MIA_FORCE_WIN_BWD"));
+    if (want_win && dbg_knob("MIA_WTMA_BWD") && plan_wtma_bwd(p, di, wt, tmaps, rgrid)) {
+        MIA_TRACE("bwd: wtma g=%d nwin=%d grid=%d smem=%d", wt.g, wt.nwin, rgrid, wt.smem_bytes);
+        wt.part_dA = a.part_dA; wt.part_dD = a.part_dD; wt.part_dbias = a.part_dbias; wt.acc_dB = a.acc_dB; wt.acc_dC = a.acc_dC;
+        bc_parts = wt.rows_per_group / 32;
+        const bool of32 = p.otype == MIA_F32 && p.itype != MIA_F32;
+        rc = dispatch(p.itype, [&](auto *tag) {
+            using T = typename std::remove_pointer<decltype(tag)>::type;
+            return (int)mia::launch_bwd_wtma<T>(tmaps, wt, rgrid, of32, stream);
+        });
+    } else if (want_win && plan_win_bwd(p, di, wb, rgrid)) {
+        MIA_TRACE("bwd: win (cp.async) nwin=%d grid=%d", wb.nwin, rgrid);
         wb.part_dA = a.part_dA; wb.part_dD = a.part_dD; wb.part_dbias = a.part_dbias; wb.acc_dB = a.acc_dB; wb.acc_dC = a.acc_dC;
         bc_parts = wb.rows_per_group / 32;
         const bool of32 = p.otype == MIA_F32 && p.itype != MIA_F32;

@@ -37,7 +37,7 @@ def _cmp(got, ref, rtol, atol, what):
                                  f"(ref max {ref.abs().max().item():.3e})")
 
 
-def _run_case(batch, dim, L, N, G, ddim, has_D, has_z, has_bias, softplus, dtype, out_float, seed=0):
+def _run_case(batch, dim, L, N, G, ddim, has_D, has_z, has_bias, softplus, dtype, out_float, seed=0, fs_mult=1.0):
     """CUDA path (through the C ABI) vs the fp64 C oracle on the same seeded inputs.  Criteria (tests/parity.py):
     tensors stored in bf16 / fp16: within 1 ulp of the oracle rounded to that dtype + 1e-3 RMS(ref);
     fp32 tensors (fp32 runs, "oflex" fp32 outputs, weight gradients, last state): rtol 1e-5 + 2e-5 RMS(ref), both times
@@ -45,7 +45,7 @@ def _run_case(batch, dim, L, N, G, ddim, has_D, has_z, has_bias, softplus, dtype
     from medical_image_analysis_b200 import scan_bwd, scan_fwd
     from oracle import ss_ref_c
     from tests.parity import cmp_auto, long_row_scale
-    fs = long_row_scale(L)
+    fs = long_row_scale(L) * fs_mult
     tag = f"[b{batch} d{dim} L{L} N{N} G{G} dd{ddim} D{int(has_D)} z{int(has_z)} bias{int(has_bias)} sp{int(softplus)} {str(dtype)[6:]} o32={int(out_float)}]"
     cpu, gpu = _inputs(seed, batch, dim, L, N, G, ddim, has_D, has_z, has_bias, dtype)
     out, x, out_z, hblk = scan_fwd(gpu["u"], gpu["delta"], gpu["A"], gpu["B"], gpu["C"], gpu["D"], gpu["z"], gpu["delta_bias"],
@@ -95,7 +95,11 @@ def test_scan_parity_small(shape, dtype, out_float):
 # for L <= 256): block-boundary, ragged-last-block and single-quad cases of the 16-token recompute blocks.
 ROWS = [(2, 64, 196, 1, 2, 64), (1, 32, 4, 1, 1, 32), (2, 96, 16, 1, 3, 96), (1, 64, 20, 1, 1, 64), (2, 64, 256, 1, 2, 64),
         (1, 32, 252, 1, 1, 32), (2, 128, 64, 1, 4, 128), (3, 32, 36, 1, 1, 32), (1, 64, 512, 1, 2, 64), (1, 32, 1000, 1, 1, 32),
-        (2, 32, 260, 1, 1, 32), (1, 64, 776, 1, 2, 64), (2, 32, 264, 1, 1, 32), (1, 32, 2048, 1, 1, 32)]
+        (2, 32, 260, 1, 1, 32), (1, 64, 776, 1, 2, 64), (2, 32, 264, 1, 1, 32), (1, 32, 2048, 1, 1, 32),
+        (2, 32, 300, 1, 1, 32), (1, 64, 292, 1, 2, 64), (3, 32, 324, 1, 1, 32),
+        # column-walk forward, two rows per tensor-map row (L * 2 bytes % 16 == 8, rows_per_group % 64 == 0)
+        (2, 128, 196, 1, 2, 128), (1, 64, 4, 1, 1, 64), (2, 64, 36, 1, 1, 64), (1, 128, 100, 1, 2, 128), (1, 64, 204, 1, 1, 64),
+        (3, 64, 12, 1, 1, 64), (1, 64, 28, 1, 1, 64)]
 
 
 @pytest.mark.parametrize("shape", ROWS, ids=[f"b{s[0]}d{s[1]}L{s[2]}G{s[4]}" for s in ROWS])
@@ -104,6 +108,14 @@ ROWS = [(2, 64, 196, 1, 2, 64), (1, 32, 4, 1, 1, 32), (2, 96, 16, 1, 3, 96), (1,
 def test_scan_parity_row_serial(shape, dtype, out_float):
     batch, dim, L, N, G, ddim = shape
     _run_case(batch, dim, L, N, G, ddim, True, False, True, True, dtype, out_float, seed=5)
+
+
+@pytest.mark.parametrize("dtype,out_float", [(torch.float32, False), (torch.bfloat16, False), (torch.bfloat16, True)], ids=["f32", "bf16", "bf16o32"])
+def test_scan_parity_column_walk_two_chunks(dtype, out_float):
+    """Column-walk forward on rows of two checkpoint chunks: it is preferred to the chunk-parallel kernel from 4 x 148 32-row
+    items on, hence the size.  5.6 M elements per tensor: the extreme tail of the fp32 error distribution reaches 1.3 x the
+    2e-5 RMS criterion calibrated on the small cases (measured: 5 elements, gpurun r2i) -> that criterion x 2 here."""
+    _run_case(19, 1024, 288, 1, 1, 1024, True, False, True, True, dtype, out_float, seed=11, fs_mult=2.0)
 
 
 # d_state 16 / 8 shapes the row-serial forward for d_state > 1 takes (whole rows in one tile; the backward is the warp-scan one)
@@ -169,9 +181,16 @@ def test_scan_golden_reference_vectors():
             if lowp and got.dtype == case["dtype"]:
                 # the stored value is the reference's fp32 autograd result rounded to bf16: its own fp32 noise can sit on the
                 # other side of a rounding boundary from the fp64-exact value the kernel tracks -> 2 ulp (measured: 1.02)
-                cmp_stored(got, ref[name], case["dtype"], f"{case['tag']}.{name}", n_ulp=2.0)
+                # z-gated cases: the reference's PYTHON function evaluates silu(z) in z's own dtype (test_selective_scan.py:231-232,
+                # bf16: a 2^-9 relative perturbation of dy = dout silu(z)) while its CUDA kernel -- and this one -- evaluate it in
+                # fp32; du / ddelta are sums of terms ~RMS that cancel, so the perturbation shows as an ABSOLUTE error of
+                # ~2^-8 RMS (measured 0.025 at RMS 1.2).  The fp32-silu semantics are pinned by the C oracle in _run_case.
+                cmp_stored(got, ref[name], case["dtype"], f"{case['tag']}.{name}", n_ulp=2.0,
+                           atol_rms=3e-2 if g["z"] is not None else 1e-3)
             else:
-                _cmp(got, ref[name], 2e-4, 2e-4 * max(1.0, ref[name].abs().max().item()), f"{case['tag']}.{name}")
+                # fp32 reductions of a z-gated low-precision case inherit the same bf16-silu perturbation (see above)
+                rt = 1e-2 if (lowp and g["z"] is not None) else 2e-4
+                _cmp(got, ref[name], rt, rt * max(1.0, ref[name].abs().max().item()), f"{case['tag']}.{name}")
 
 
 def test_c1_config():
@@ -253,7 +272,7 @@ def test_scan_strided_inputs():
 @pytest.mark.parametrize("use_hblk", [False, True])
 def test_bwd_is_deterministic_dstate1(use_hblk):
     from medical_image_analysis_b200 import scan_bwd, scan_fwd
-    _, g = _inputs(9, 4, 96, 300, 1, 2, 96, True, False, True, torch.bfloat16)
+    _, g = _inputs(9, 4, 128, 300, 1, 2, 128, True, False, True, torch.bfloat16)
     out, x, _, hblk = scan_fwd(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"], None, g["delta_bias"], True, True, want_block_states=True)
     assert hblk is not None
     hb = hblk if use_hblk else None
