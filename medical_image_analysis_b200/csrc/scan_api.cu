@@ -13,6 +13,7 @@
 #include "scan_bwd_rowsn.cuh"
 #include "scan_bwd_win.cuh"
 #include "scan_bwd_wtma.cuh"
+#include "scan_bwd_cw.cuh"
 #include "tma_host.h"
 #include "scan_fwd_rowsn.cuh"
 #include "scan_fwd_stream.cuh"
@@ -28,6 +29,7 @@ template <typename T> cudaError_t launch_fwd_cw(const CUtensorMap *, const CwFwd
 template <typename T> cudaError_t launch_bwd_rows(const RowsBwdArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_rowsn(const RowsNBwdArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_win(const WinBwdArgs &, int, bool, cudaStream_t);
+template <typename T> cudaError_t launch_bwd_cw(const CUtensorMap *, const CwBwdArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_wtma(const CUtensorMap *, const WinTmaArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_fwd_any(const ScanArgs &, int, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_any(const ScanArgs &, int, cudaStream_t);
@@ -652,6 +654,51 @@ bool plan_wtma_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::WinTmaArgs
     return true;
 }
 
+// Column-walk backward (scan_bwd_cw.cuh): eligibility, argument block, tensor maps (u, delta, dout, du, ddelta).
+bool plan_cw_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::CwBwdArgs &r, CUtensorMap *tm, int &grid) {
+    const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
+    int g = 0;
+    if (!p.hblk || !cw_geometry(p, g)) return false;
+    if (dbg_knob("MIA_NO_CW_BWD")) return false;
+    const int rpg = p.dim / p.n_groups;
+    auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
+    if (!dense(p.u_batch_stride, p.u_d_stride) || !dense(p.delta_batch_stride, p.delta_d_stride) ||
+        !dense(p.dout_batch_stride, p.dout_d_stride) || !dense(p.du_batch_stride, p.du_d_stride) ||
+        !dense(p.ddelta_batch_stride, p.ddelta_d_stride)) return false;
+    if (p.A_d_stride != 1 && p.dim > 1) return false;
+    if (((uintptr_t)p.u | (uintptr_t)p.delta | (uintptr_t)p.dout | (uintptr_t)p.du | (uintptr_t)p.ddelta) & 15) return false;
+    const unsigned long long trows = (unsigned long long)p.batch * p.dim / g, tcols = (unsigned long long)g * L;
+    if (tcols >= (1ull << 31) || trows >= (1ull << 31)) return false;
+    memset(&r, 0, sizeof(r));
+    r.batch = p.batch; r.dim = p.dim; r.L = L; r.G = p.n_groups; r.rows_per_group = rpg; r.softplus = p.delta_softplus;
+    r.g = g;
+    r.n_items = p.batch * p.n_groups * (rpg / (32 * g));
+    r.ngrp = (g * L + mia::kCwGrp - 1) / mia::kCwGrp;
+    const int tile_i = 32 * mia::kCwGrp * es, tile_o = 32 * mia::kCwGrp * eo;
+    r.stage_bytes = 2 * tile_i + tile_o;
+    r.ns = dbg_int("MIA_CW_STAGES", 4);
+    r.off_bc32 = r.ns * r.stage_bytes;
+    r.off_pf = r.off_bc32 + 2 * mia::kCwGrp * 4;                // two 256-byte prefetch slots (raw B, raw C, block states)
+    r.off_bar = r.off_pf + 512;
+    r.smem_bytes = r.off_bar + 8 * r.ns + 16 + 1024;            // + slack for the 1024-byte alignment of the tiles
+    if ((((uintptr_t)p.B | (uintptr_t)p.C) & 3) || ((p.B_batch_stride | p.B_group_stride | p.C_batch_stride | p.C_group_stride) * es) % 4) return false;
+    r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.hblk = p.hblk;
+    r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride;
+    const void *ptrs[5] = {p.u, p.delta, p.dout, p.du, p.ddelta};
+    for (int i = 0; i < 5; ++i) {
+        const int e = i == 2 ? eo : es;
+        const int trc = mia::tma_make_2d(&tm[i], ptrs[i], trows, tcols, tcols * e, 32, mia::kCwGrp, e, mia::kCwGrp * e);
+        if (trc != 0) { MIA_TRACE("cw bwd: tensor map %d rejected (CUresult %d)", i, trc); return false; }
+    }
+    int per_sm = (227 * 1024) / (r.smem_bytes + 1024);
+    if (per_sm > 16) per_sm = 16;
+    if (per_sm < 1) return false;
+    const long long slots = (long long)di.sms * per_sm;
+    const long long rounds = (r.n_items + slots - 1) / slots;
+    grid = (int)((r.n_items + rounds - 1) / rounds);             // equal rounds per CTA
+    return true;
+}
+
 // Deterministic d_state 16 backward (scan_bwd_rowsn.cuh): eligibility + argument block.
 bool plan_rowsn_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsNBwdArgs &r, int &grid) {
     const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
@@ -1002,7 +1049,18 @@ int mia_selective_scan_bwd(const mia_ss_params *pp, void *cuda_stream) {
     const long long items32 = (long long)p.batch * (p.dim / 32);
     const bool want_win = !use_rowsn && hblk_std &&
                           ((p.seqlen > mia::kRowsChunk && items32 >= 4LL * di.sms) || dbg_knob("MIA_FORCE_WIN_BWD"));
-    if (want_win && dbg_knob("MIA_WTMA_BWD") && plan_wtma_bwd(p, di, wt, tmaps, rgrid)) {
+    mia::CwBwdArgs cwb;
+    const bool want_cw = !use_rowsn && p.hblk && (items32 >= 4LL * di.sms || dbg_knob("MIA_FORCE_CW_BWD"));
+    if (want_cw && plan_cw_bwd(p, di, cwb, tmaps, rgrid)) {
+        MIA_TRACE("bwd: cw g=%d ns=%d ngrp=%d grid=%d smem=%d", cwb.g, cwb.ns, cwb.ngrp, rgrid, cwb.smem_bytes);
+        cwb.part_dA = a.part_dA; cwb.part_dD = a.part_dD; cwb.part_dbias = a.part_dbias; cwb.acc_dB = a.acc_dB; cwb.acc_dC = a.acc_dC;
+        bc_parts = cwb.rows_per_group / 32;
+        const bool of32 = p.otype == MIA_F32 && p.itype != MIA_F32;
+        rc = dispatch(p.itype, [&](auto *tag) {
+            using T = typename std::remove_pointer<decltype(tag)>::type;
+            return (int)mia::launch_bwd_cw<T>(tmaps, cwb, rgrid, of32, stream);
+        });
+    } else if (want_win && dbg_knob("MIA_WTMA_BWD") && plan_wtma_bwd(p, di, wt, tmaps, rgrid)) {
         MIA_TRACE("bwd: wtma g=%d nwin=%d grid=%d smem=%d", wt.g, wt.nwin, rgrid, wt.smem_bytes);
         wt.part_dA = a.part_dA; wt.part_dD = a.part_dD; wt.part_dbias = a.part_dbias; wt.acc_dB = a.acc_dB; wt.acc_dC = a.acc_dC;
         bc_parts = wt.rows_per_group / 32;

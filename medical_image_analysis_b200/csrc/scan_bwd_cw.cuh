@@ -1,0 +1,379 @@
+// Backward selective scan, COLUMN-WALK row-serial path (d_state == 1) on the block states the column-walk forward leaves
+// (scan_fwd_cw.cuh): one lane per row, phase 2 only (no forward re-walk), the row walked from its end in 16-column groups.
+//
+// Why another backward (measured, gpurun r2f / r2i; ncu of the resident-row kernel, profiles/): scan_bwd_rows.cuh and
+// scan_bwd_win.cuh run at 41-43 % issue utilisation with 10-12 warps per SM -- 168 registers per thread (seven 16-token
+// quantities kept from the recompute to the suffix loop) and still ~300 bytes of spills (long-scoreboard stalls), a two-warp
+// barrier, ~170 instructions of 8-byte cp.async pieces per window.  Here
+//   * a group (16 columns of 32 rows) of u, delta and dout is one TMA box each, through a 4-stage ring: lane 0 issues three
+//     box loads per group, three groups ahead; du / ddelta replace u / delta in the stage and leave with two box stores; a
+//     stage is refilled one step after its stores were committed (cp.async.bulk.wait_group.read 1), so nobody waits;
+//   * only a, a h_{t-1} and m (softplus) survive the recompute (48 registers instead of 112): the other per-token factors are
+//     re-derived in the suffix loop from them and from u / B, which are still in the stage; dC is reduced over the rows right
+//     after the recompute and dB after the suffix loop (two 16-value butterflies, 32 shuffles, instead of one of 32 values);
+//   * 128 registers, ~13 KB of shared memory per warp: 15-16 resident one-warp CTAs per SM, no barrier.
+// Rows of 392 bytes (L = 196 bf16) are walked two to a tensor-map row (g = 2) exactly like the forward: the odd row first
+// (columns [L, 2 L) from the end), then the even row; the group that holds column L is split between them.
+// Reductions over rows (dB, dC): the same transposing butterfly as scan_bwd_rows.cuh, one partial per (32 rows, token) in the
+// workspace, folded in a fixed order by the finalize kernel -> deterministic.
+// Preconditions (host-checked): as scan_fwd_cw.cuh, block states present, dense 16-byte aligned u / delta / dout / du / ddelta.
+#pragma once
+#include <cuda.h>
+
+#include <type_traits>
+
+#include "scan_bwd_rows.cuh"
+#include "scan_fwd_cw.cuh"
+#include "scan_fwd_stream.cuh"
+
+namespace mia {
+
+constexpr int kCwGrp = 16;       // columns per group = tokens per recompute block
+
+struct CwBwdArgs {
+    int batch, dim, L, G, rows_per_group;
+    int softplus;
+    int g, n_items, ngrp, ns;               // rows per tensor-map row; items of 32 g rows; 16-column groups per tensor-map row; stages
+    int stage_bytes, off_bc32, off_pf, off_bar, smem_bytes;
+    const void *A, *B, *C, *D, *delta_bias;
+    const float *hblk;
+    float *part_dA, *part_dD, *part_dbias, *acc_dB, *acc_dC;
+    long long B_bs, B_gs, C_bs, C_gs;
+};
+
+// tile rows of 32 bytes (16 two-byte columns): CU_TENSOR_MAP_SWIZZLE_32B (16-byte chunk index ^= address bit 7)
+template <int RB>
+__device__ __forceinline__ SwzRow swz_row_any(int row) {
+    if constexpr (RB == 32) {
+        const uint32_t off = (uint32_t)(row * 32);
+        SwzRow r;
+        r.line = off & ~127u;
+        r.y = (off & 127u) ^ (((off >> 7) & 1u) << 4);
+        return r;
+    } else {
+        return swz_row<RB>(row);
+    }
+}
+
+struct CwRegs {
+    float2 a[8], hp[8], m[8];      // a_t, a_t h_{t-1}, softplus(delta + bias) log2e of the 16 tokens
+};
+
+// Sum each of 16 per-lane values over the 32 lanes: transposing butterfly (strides 8, 4, 2, 1: a lane keeps the half of its
+// values whose index has that bit equal to its own lane bit, summed with the partner's copy), then the two 16-lane halves are
+// added.  16 shuffles; lane i ends with the warp total of v[i & 15] in v[0].
+__device__ __forceinline__ void butterfly16(float (&v)[16], const int lane) {
+#pragma unroll
+    for (int s = 8; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float send = up ? v[i] : v[i + s];
+            const float keep = up ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
+// One group (or the part of it that belongs to one row): quads [qlo, qhi) of the 16 columns.  tok0: token of the group's
+// first column in the current row (negative for the odd row's head); h0: state entering quad qlo.
+template <typename T, typename TO, bool kSoftplus, bool kFull>
+__device__ __forceinline__ void cw_bwd_block(const int qlo_in, const int qhi_in, const int tok0, const int lane, const float h0, char *tu, char *td,
+                                             const char *to, const SwzRow ri, const SwzRow ro, const float *Bf, const float *Cf, float *accB,
+                                             float *accC, const float2 bl2, const float2 A2, const float2 Aln2, const float2 D2, float &G,
+                                             float2 &dA2, float2 &dD2, float2 &db2) {
+    constexpr int es = (int)sizeof(T), eo = (int)sizeof(TO);
+    const int qlo = kFull ? 0 : qlo_in, qhi = kFull ? 4 : qhi_in;
+    const float2 kL2E = splat2(kLog2e), kOne = splat2(1.f);
+    const int i16 = lane & 15;
+    const bool mine = kFull || (i16 >= 4 * qlo && i16 < 4 * qhi);       // this lane's butterfly slot is a token of the block
+    CwRegs R;
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    float h = h0;
+    // ---- recompute a, a h_{t-1}, m of the block from the state entering it; dC_t = sum over rows of dy_t h_t on the way
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (kFull || (q >= qlo && q < qhi)) {
+            float2 dd[2], uu[2], Bv[2], dy[2];
+            Quad<T>::ld(td + ri.at(4 * q * es), dd);
+            Quad<T>::ld(tu + ri.at(4 * q * es), uu);
+            Quad<float>::ld(reinterpret_cast<const char *>(Bf + 4 * q), Bv);
+            Quad<TO>::ld(to + ro.at(4 * q * eo), dy);
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const int k = 2 * q + p;
+                float2 m = fma2(dd[p], kL2E, bl2);                      // (delta + bias) log2e
+                if (kSoftplus) {
+                    const float2 e = make_float2(ex2f(fminf(m.x, 120.f)), ex2f(fminf(m.y, 120.f)));
+                    const float2 s = add2(e, kOne);
+                    m = make_float2(fmaxf(lg2f(s.x), m.x), fmaxf(lg2f(s.y), m.y));   // softplus log2e
+                }
+                const float2 av = ex2_2(mul2(m, A2));
+                const float2 bv = mul2(mul2(m, uu[p]), Bv[p]);
+                float2 hp, hh;
+                hp.x = av.x * h; h = hp.x + bv.x; hh.x = h;             // a_t h_{t-1}, then h_t
+                hp.y = av.y * h; h = hp.y + bv.y; hh.y = h;
+                R.a[k] = av; R.hp[k] = hp; R.m[k] = m;
+                const float2 dCv = mul2(dy[p], hh);
+                v[2 * k] = dCv.x; v[2 * k + 1] = dCv.y;
+            }
+        }
+    }
+    butterfly16(v, lane);
+    if (mine && lane < 16) accC[tok0 + i16] = v[0];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    // ---- suffix recurrence G_t = a_t (dy_t C_t + G_{t+1}), gradients of the block
+#pragma unroll
+    for (int q = 3; q >= 0; --q) {
+        if (kFull || (q >= qlo && q < qhi)) {
+            float2 dy[2], Cv[2], Bv[2], uu[2], du[2], dd[2];
+            Quad<TO>::ld(to + ro.at(4 * q * eo), dy);
+            Quad<float>::ld(reinterpret_cast<const char *>(Cf + 4 * q), Cv);
+            Quad<float>::ld(reinterpret_cast<const char *>(Bf + 4 * q), Bv);
+            Quad<T>::ld(tu + ri.at(4 * q * es), uu);                    // u is still in the stage (du is written below)
+#pragma unroll
+            for (int p = 1; p >= 0; --p) {
+                const int k = 2 * q + p;
+                const float2 pc = mul2(dy[p], Cv[p]);
+                const float2 ap = mul2(R.a[k], pc);
+                float2 gg;
+                gg.y = pc.y + G; G = fmaf(R.a[k].y, G, ap.y);
+                gg.x = pc.x + G; G = fmaf(R.a[k].x, G, ap.x);
+                const float2 dBv = mul2(gg, mul2(R.m[k], uu[p]));
+                v[2 * k] = dBv.x; v[2 * k + 1] = dBv.y;
+                float2 sg = kL2E;                                       // d m / d (delta + bias) = sigmoid log2e = (1 - 2^-m) log2e
+                if (kSoftplus) sg = fma2(ex2_2(make_float2(-R.m[k].x, -R.m[k].y)), make_float2(-kLog2e, -kLog2e), kL2E);
+                const float2 qv = fma2(R.hp[k], Aln2, mul2(uu[p], Bv[p]));   // ln2 d h_t / d m_t
+                du[p] = fma2(gg, mul2(R.m[k], Bv[p]), mul2(dy[p], D2));
+                dd[p] = mul2(gg, mul2(qv, sg));
+                db2 = add2(db2, dd[p]);
+                dA2 = fma2(gg, mul2(R.m[k], R.hp[k]), dA2);
+                dD2 = fma2(dy[p], uu[p], dD2);
+            }
+            Quad<T>::st(tu + ri.at(4 * q * es), du);                    // du replaces u, ddelta replaces delta
+            Quad<T>::st(td + ri.at(4 * q * es), dd);
+        }
+    }
+    butterfly16(v, lane);
+    if (mine && lane < 16) accB[tok0 + i16] = v[0] * kLn2;
+}
+
+template <typename T, bool kSoftplus, bool kOutF32, int kG>
+__global__ void __launch_bounds__(32, 12) ss_bwd_cw_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_d,
+                                                           const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_du,
+                                                           const __grid_constant__ CUtensorMap tm_dd, const __grid_constant__ CwBwdArgs a) {
+    extern __shared__ char smem_raw[];
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array (a cast through an integer would make every tile
+    // access a generic LD / ST instead of LDS / STS)
+    char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int es = (int)sizeof(T);
+    constexpr int eo = kOutF32 ? 4 : es;
+    using TO = typename std::conditional<kOutF32, float, T>::type;
+    using raw = typename Cvt<T>::raw;
+    constexpr int RBi = kCwGrp * es, RBo = kCwGrp * eo;                  // tile row bytes: 32 or 64
+    constexpr int kTileI = 32 * RBi, kTileO = 32 * RBo;
+    const int lane = threadIdx.x;
+    float *Bw = reinterpret_cast<float *>(smem + a.off_bc32), *Cw = Bw + kCwGrp;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + a.off_bar);
+    const int ns = a.ns;
+    if (lane == 0) {
+        for (int s = 0; s < ns; ++s) mbar_init(full + s, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    const int L = a.L, ncols = kG * L, ngrp = a.ngrp;
+    const int rows_per_item = 32 * kG;
+    const int items_per_group = a.rows_per_group / rows_per_item;
+    const float *Ap = reinterpret_cast<const float *>(a.A);
+    const float *Dp = reinterpret_cast<const float *>(a.D);
+    const float *biasp = reinterpret_cast<const float *>(a.delta_bias);
+    const SwzRow ri = swz_row_any<RBi>(lane), ro = swz_row_any<RBo>(lane);
+
+    auto item_rows = [&](int item, int &b, int &gq, int &row0) {
+        const int bt = item % items_per_group;
+        const int bg = item / items_per_group;
+        gq = bg % a.G; b = bg / a.G;
+        row0 = gq * a.rows_per_group + bt * rows_per_item;
+    };
+
+    // ---- load stream: (item, group) pairs in the order this CTA computes them (groups from the last one down), ns - 1 ahead
+    int ld_item = blockIdx.x, ld_j = ngrp - 1, ld_srow0 = 0, ld_stage = 0;
+    if (ld_item < a.n_items) { int b, gq, r0; item_rows(ld_item, b, gq, r0); ld_srow0 = (b * a.dim + r0) / kG; }
+    auto issue_load = [&]() {                                           // lane 0 only; no-op past the last item
+        if (ld_item < a.n_items) {
+            char *st = smem + ld_stage * a.stage_bytes;
+            mbar_arrive_expect_tx(full + ld_stage, 2u * kTileI + kTileO);
+            tma_box_g2s(st, &tm_u, ld_j * kCwGrp, ld_srow0, full + ld_stage);
+            tma_box_g2s(st + kTileI, &tm_d, ld_j * kCwGrp, ld_srow0, full + ld_stage);
+            tma_box_g2s(st + 2 * kTileI, &tm_o, ld_j * kCwGrp, ld_srow0, full + ld_stage);
+            if (--ld_j < 0) {
+                ld_j = ngrp - 1;
+                ld_item += gridDim.x;
+                if (ld_item < a.n_items) { int b, gq, r0; item_rows(ld_item, b, gq, r0); ld_srow0 = (b * a.dim + r0) / kG; }
+            }
+        }
+        ld_stage = ld_stage + 1 == ns ? 0 : ld_stage + 1;
+    };
+    if (lane == 0)
+        for (int s = 0; s < ns - 1; ++s) issue_load();
+
+    uint32_t phbits = 0;
+    int stage = 0;
+    // B / C elements and block states of the group about to be computed: prefetched one step ahead by 4-byte cp.async into a
+    // two-slot ring in shared memory (NOT into registers: a register live across a block gets spilled, and the spill store waits
+    // for the load -- measured: the dominant stall of the first version).  Slot: [raw B 64 B][raw C 64 B][32 block states].
+    constexpr int kEpw = 4 / es, kNw = kCwGrp / kEpw;                    // elements per 4-byte word, words per 16 columns
+    char *pf = smem + a.off_pf;
+    const raw *gBC = nullptr;                                            // this lane's B or C row of the item the prefetch is in
+    const float *gh = nullptr;
+    auto bc_rows = [&](int item) {
+        if (item < a.n_items) {
+            int b, gq, r0;
+            item_rows(item, b, gq, r0);
+            gBC = lane < kNw ? reinterpret_cast<const raw *>(a.B) + (size_t)b * a.B_bs + (size_t)gq * a.B_gs
+                             : reinterpret_cast<const raw *>(a.C) + (size_t)b * a.C_bs + (size_t)gq * a.C_gs;
+            gh = a.hblk + (size_t)item * ngrp * 32 + lane;
+        } else {
+            gBC = nullptr;
+        }
+    };
+    int pslot = 0;
+    auto prefetch = [&](int j) {                                         // into slot `pslot`
+        char *sl = pf + pslot * 256;
+        if (lane < 2 * kNw) {
+            const int wd = lane < kNw ? lane : lane - kNw;
+            const int c = j * kCwGrp + wd * kEpw;
+            const int tk = (kG == 2 && c >= L) ? c - L : c;              // token of column c (pairs never straddle L: both even)
+            const bool ok = gBC != nullptr && c < ncols;
+            const uint32_t n = ok ? 4u : 0u;                             // src-size 0: zero fill
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(sl + (lane < kNw ? 0 : 64) + wd * 4)),
+                         "l"(ok ? (const void *)(gBC + tk) : (const void *)a.hblk), "r"(n)
+                         : "memory");
+        }
+        {
+            const bool ok = gBC != nullptr && j > 0;
+            const uint32_t n = ok ? 4u : 0u;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(sl + 128 + lane * 4)),
+                         "l"(ok ? (const void *)(gh + j * 32) : (const void *)a.hblk), "r"(n)
+                         : "memory");
+        }
+        cp_async_commit();
+    };
+    bc_rows(blockIdx.x);
+    prefetch(ngrp - 1);
+
+    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+        int b, gq, row0;
+        item_rows(item, b, gq, row0);
+        const int srow0 = (b * a.dim + row0) / kG;
+        int seg = kG - 1;                                                // the last row of the tensor-map row first
+        int d = row0 + kG * lane + seg;
+        float Araw = __ldg(Ap + d);
+        float2 bl2 = splat2((biasp ? __ldg(biasp + d) : 0.f) * kLog2e), A2 = splat2(Araw), Aln2 = splat2(Araw * kLn2),
+               D2 = splat2(Dp ? __ldg(Dp + d) : 0.f);
+        float2 dA2 = make_float2(0.f, 0.f), dD2 = dA2, db2 = dA2;
+        float G = 0.f;
+        float *accB = a.acc_dB + ((size_t)item * kG + seg) * L, *accC = a.acc_dC + ((size_t)item * kG + seg) * L;
+        auto flush_row = [&]() {
+            a.part_dA[(size_t)b * a.dim + d] = (dA2.x + dA2.y) * kLn2;
+            a.part_dD[(size_t)b * a.dim + d] = dD2.x + dD2.y;
+            a.part_dbias[(size_t)b * a.dim + d] = db2.x + db2.y;
+        };
+
+        for (int j = ngrp - 1; j >= 0; --j) {
+            const int cb = j * kCwGrp;
+            // B' = B ln2 (lanes 0-15 -> Bw), C (lanes 16-31 -> Cw) of this group's 16 columns, zero past the end; block state
+            cp_async_wait<0>();
+            __syncwarp();
+            float hslot;
+            {
+                const char *sl = pf + pslot * 256;
+                const raw rv = *reinterpret_cast<const raw *>(sl + (lane < 16 ? 0 : 64) + (lane & 15) * es);
+                const float f = Cvt<T>::to_f(rv);
+                Bw[lane] = lane < 16 ? f * kLn2 : f;                     // Cw == Bw + 16
+                hslot = *reinterpret_cast<const float *>(sl + 128 + lane * 4);
+            }
+            pslot ^= 1;
+            if (j > 0) {
+                prefetch(j - 1);
+            } else {
+                bc_rows(item + gridDim.x);
+                prefetch(ngrp - 1);
+            }
+            __syncwarp();
+            mbar_wait(full + stage, (phbits >> stage) & 1u);
+            phbits ^= 1u << stage;
+            char *tu = smem + stage * a.stage_bytes, *td = tu + kTileI;
+            const char *to = tu + 2 * kTileI;
+            const int qend = min(4, (ncols - cb) / 4);                   // quads of this group inside the tensor-map row
+            const bool split = kG == 2 && cb < L && cb + kCwGrp > L;     // the group holds the end of the even row and the start of the odd one
+            if (!split && qend == 4) {
+                const int tok0 = cb - seg * L;
+                cw_bwd_block<T, TO, kSoftplus, true>(0, 4, tok0, lane, tok0 == 0 ? 0.f : hslot, tu, td, to, ri, ro, Bw, Cw, accB, accC, bl2, A2, Aln2,
+                                                     D2, G, dA2, dD2, db2);
+            } else {
+                // partial group (end of the tensor-map row), or the split group: quads [qe, qend) are the head of the odd row
+                // (processed first), [0, qe) the tail of the even row
+                const int qe = split ? (L - cb) / 4 : 0;
+                for (int part = split ? 0 : 1; part < 2; ++part) {
+                    int qlo, qhi, tok0;
+                    float h0;
+                    if (split && part == 0) {
+                        qlo = qe; qhi = qend; tok0 = cb - L; h0 = 0.f;
+                    } else if (split) {
+                        flush_row();
+                        seg = 0; d -= 1;                                 // even row: fresh suffix state, its own A / D / bias
+                        Araw = __ldg(Ap + d);
+                        bl2 = splat2((biasp ? __ldg(biasp + d) : 0.f) * kLog2e); A2 = splat2(Araw); Aln2 = splat2(Araw * kLn2);
+                        D2 = splat2(Dp ? __ldg(Dp + d) : 0.f);
+                        dA2 = make_float2(0.f, 0.f); dD2 = dA2; db2 = dA2; G = 0.f;
+                        accB -= L; accC -= L;
+                        qlo = 0; qhi = qe; tok0 = cb; h0 = cb == 0 ? 0.f : hslot;
+                    } else {
+                        qlo = 0; qhi = qend; tok0 = cb - seg * L; h0 = tok0 == 0 ? 0.f : hslot;
+                    }
+                    cw_bwd_block<T, TO, kSoftplus, false>(qlo, qhi, tok0, lane, h0, tu, td, to, ri, ro, Bw, Cw, accB, accC, bl2, A2, Aln2, D2, G, dA2,
+                                                          dD2, db2);
+                }
+            }
+            // ---- du / ddelta leave with two box stores; then the stage computed one step earlier is refilled
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                tma_box_s2g(&tm_du, tu, cb, srow0);
+                tma_box_s2g(&tm_dd, td, cb, srow0);
+                bulk_commit();
+                bulk_wait_read<1>();
+                issue_load();
+            }
+            stage = stage + 1 == ns ? 0 : stage + 1;
+        }
+        flush_row();
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <typename T, int kG>
+cudaError_t launch_bwd_cw_g(const CUtensorMap *tm, const CwBwdArgs &a, int grid, bool dout_f32, cudaStream_t stream) {
+    void (*kernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CwBwdArgs);
+    if (a.softplus) kernel = dout_f32 ? &ss_bwd_cw_kernel<T, true, true, kG> : &ss_bwd_cw_kernel<T, true, false, kG>;
+    else kernel = dout_f32 ? &ss_bwd_cw_kernel<T, false, true, kG> : &ss_bwd_cw_kernel<T, false, false, kG>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, 32, a.smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], a);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_bwd_cw(const CUtensorMap *tm, const CwBwdArgs &a, int grid, bool dout_f32, cudaStream_t stream) {
+    if constexpr (sizeof(T) == 2) {
+        if (a.g == 2) return launch_bwd_cw_g<T, 2>(tm, a, grid, dout_f32, stream);
+    }
+    return a.g == 1 ? launch_bwd_cw_g<T, 1>(tm, a, grid, dout_f32, stream) : cudaErrorInvalidValue;
+}
+
+}  // namespace mia

@@ -76,7 +76,9 @@ template <typename T, bool kSoftplus, bool kOutF32, int kG>
 __global__ void __launch_bounds__(32, 16) ss_fwd_cw_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_d,
                                                            const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CwFwdArgs a) {
     extern __shared__ char smem_raw[];
-    char *smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array (a cast through an integer would make every tile
+    // access a generic LD / ST instead of LDS / STS)
+    char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr int es = (int)sizeof(T);
     constexpr int eo = kOutF32 ? 4 : es;
     using TO = typename std::conditional<kOutF32, float, T>::type;

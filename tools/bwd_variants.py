@@ -29,8 +29,11 @@ def build_debug():
 
 VARIANTS = {
     "default": {},
-    "wtma_forced": {"MIA_FORCE_WIN_BWD": "1"},
-    "win_cpasync": {"MIA_FORCE_WIN_BWD": "1", "MIA_NO_WTMA_BWD": "1"},
+    "cw_forced": {"MIA_FORCE_CW_BWD": "1"},
+    "cw_3stages": {"MIA_FORCE_CW_BWD": "1", "MIA_CW_STAGES": "3"},
+    "cw_6stages": {"MIA_FORCE_CW_BWD": "1", "MIA_CW_STAGES": "6"},
+    "no_cw": {"MIA_NO_CW_BWD": "1"},
+    "win_cpasync": {"MIA_NO_CW_BWD": "1", "MIA_FORCE_WIN_BWD": "1"},
     "no_hblk": None,          # backward without block states: resident-row / warp-scan kernels
 }
 
@@ -91,7 +94,7 @@ def main():
         out, x, _, hblk = scan_fwd(u, delta, A, Bm, Cm, Dv, None, bias, True, of32, want_block_states=True)
         base = None
         for name, env in VARIANTS.items():
-            for k in ("MIA_FORCE_WIN_BWD", "MIA_NO_WTMA_BWD", "MIA_NO_WIN_BWD"):
+            for k in ("MIA_FORCE_WIN_BWD", "MIA_NO_WTMA_BWD", "MIA_NO_WIN_BWD", "MIA_FORCE_CW_BWD", "MIA_NO_CW_BWD", "MIA_CW_STAGES"):
                 os.environ.pop(k, None)
             if env:
                 os.environ.update(env)
