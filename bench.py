@@ -599,7 +599,7 @@ def main():
     dom = max(range(len(ws)), key=lambda i: bwd_ms[i])          # dominant kernel = the backward call with the largest time share
     step_bytes = sum(tk * (f + b) for tk, (f, b) in zip(tokens, bpt))
     step_gbs = step_bytes / (total_ms / args.steps * 1e-3) / 1e9
-    bwd_kernel = {1: "ss_bwd_rows_kernel<bf16> (or ss_bwd_fast for rows the row-serial kernel does not take)", 16: "ss_bwd_rowsn_kernel<bf16>"}
+    bwd_kernel = {1: "ss_bwd_cw_kernel<bf16> (column-walk, scan_bwd_cw.cuh)", 16: "ss_bwd_rowsn_kernel<bf16>"}
     traffic, traffic_src = ncu_traffic("bwd", ws[dom]["B"]) if names[dom] == DEFAULT else (None, None)
     roofline = {"bound": "hbm",
                 "kernel": "backward C-ABI call of %s = %s + ss_finalize_kernel (timed together, CUDA events in the timed region)"

@@ -98,10 +98,10 @@ typedef struct mia_ss_params {
     size_t workspace_bytes;
 
     /* ---- (ABI 2) optional block states handed from fwd to the matching bwd: mia_ss_block_state_floats(p) floats, 128-byte
-     * aligned, or NULL.  The d_state == 1 row-serial forward kernels write the state entering every 16-token block of
-     * every row here (when mia_ss_fwd_writes_block_states(p) != 0); given to the backward of the SAME inputs it lets the
-     * windowed kernel (csrc/scan_bwd_win.cuh) skip the forward recompute pass.  NULL on either side = the resident-row /
-     * warp-scan kernels, same results. */
+     * aligned, or NULL.  The d_state == 1 column-walk forward (csrc/scan_fwd_cw.cuh) writes the state entering every group of
+     * 16 tokens of every row here (when mia_ss_fwd_writes_block_states(p) != 0; the layout is the kernel pair's own, see
+     * that file); given to the backward of the SAME inputs it lets the column-walk backward (csrc/scan_bwd_cw.cuh) skip
+     * the forward recompute pass.  NULL on either side = the resident-row / warp-scan kernels, same results. */
     float *hblk;
 } mia_ss_params;
 

@@ -1,6 +1,7 @@
 // Host side of libmia_scan.so: argument validation (the reference's TORCH_CHECKs,
 // selective_scan_oflex.cpp:152-204 / 245-312), tile planning, launches, the finalize kernel that folds the
 // backward's deterministic partials, and the extern "C" surface declared in include/mia_selective_scan.h.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -11,8 +12,6 @@
 #include "scan_common.cuh"
 #include "scan_bwd_rows.cuh"
 #include "scan_bwd_rowsn.cuh"
-#include "scan_bwd_win.cuh"
-#include "scan_bwd_wtma.cuh"
 #include "scan_bwd_cw.cuh"
 #include "tma_host.h"
 #include "scan_fwd_rowsn.cuh"
@@ -28,9 +27,7 @@ template <typename T> cudaError_t launch_fwd_chunks(const ChunkArgs &, int, bool
 template <typename T> cudaError_t launch_fwd_cw(const CUtensorMap *, const CwFwdArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_rows(const RowsBwdArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_rowsn(const RowsNBwdArgs &, int, bool, cudaStream_t);
-template <typename T> cudaError_t launch_bwd_win(const WinBwdArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_cw(const CUtensorMap *, const CwBwdArgs &, int, bool, cudaStream_t);
-template <typename T> cudaError_t launch_bwd_wtma(const CUtensorMap *, const WinTmaArgs &, int, bool, cudaStream_t);
 template <typename T> cudaError_t launch_fwd_any(const ScanArgs &, int, cudaStream_t);
 template <typename T> cudaError_t launch_bwd_any(const ScanArgs &, int, cudaStream_t);
 }  // namespace mia
@@ -333,11 +330,6 @@ bool plan_rows_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsArgs &
     if (r.smem_bytes > di.smem_optin) return false;
     r.xchunks = mia_ss_num_chunks(L); r.xchunk_tokens = mia_ss_chunk_len(L);
     r.u = p.u; r.delta = p.delta; r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.out = p.out; r.x = p.x;
-    r.hblk = p.hblk; r.nblk16 = (L + 15) / 16;
-    {
-        int g = 0;
-        if (cw_geometry(p, g) && g == 2) r.hblk = nullptr;      // block states of such shapes have the column-walk layout: not ours to write
-    }
     r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride;
     const int per_sm = di.smem_optin / (r.smem_bytes + 1024) > 0 ? (227 * 1024) / (r.smem_bytes + 1024) : 1;
     grid = di.sms * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
@@ -400,6 +392,7 @@ bool plan_cw_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::CwFwdArgs &r
     }
     int per_sm = (227 * 1024) / (r.smem_bytes + 1024);
     if (per_sm > 16) per_sm = 16;
+    per_sm = std::min(per_sm, dbg_int("MIA_CW_MAXPERSM", per_sm));
     if (per_sm < 1) return false;
     const long long slots = (long long)di.sms * per_sm;
     const long long rounds = (n_items + slots - 1) / slots;
@@ -435,7 +428,6 @@ bool plan_chunks_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::ChunkArg
     if (per_sm < 3) return false;
     if (per_sm > 8) per_sm = 8;
     r.u = p.u; r.delta = p.delta; r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.out = p.out; r.x = p.x;
-    r.hblk = p.hblk; r.nblk16 = (L + 15) / 16;
     r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride;
     grid = di.sms * per_sm;
     if (grid > r.n_items) grid = r.n_items;
@@ -561,99 +553,6 @@ bool plan_rows_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsBwdArg
     return true;
 }
 
-// Windowed row-serial backward on forward-provided block states (scan_bwd_win.cuh): eligibility + argument block.
-bool plan_win_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::WinBwdArgs &r, int &grid) {
-    const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
-    const int rpg = p.dim / p.n_groups;
-    if (!p.hblk || p.dstate != 1 || p.z || p.delta_dim != p.dim || (rpg % 32) || (L % 4)) return false;
-    if (dbg_knob("MIA_NO_WIN_BWD")) return false;
-    // Measured on B200 (gpurun r2e): L = 6400, B = 16: 1.17 ms vs 1.78 ms for the warp-scan kernel (and no per-CTA residency
-    // condition); L = 196, B = 148: 0.43 ms vs 0.37 ms for the resident-row kernel (7 windows of which the last holds 4
-    // tokens, 8-byte cp.async pieces) -> rows of more than one 256-token chunk only, unless forced for the tests.
-    if (L <= mia::kRowsChunk && !dbg_knob("MIA_FORCE_WIN_BWD")) return false;
-    auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
-    if (!dense(p.u_batch_stride, p.u_d_stride) || !dense(p.delta_batch_stride, p.delta_d_stride) ||
-        !dense(p.dout_batch_stride, p.dout_d_stride) || !dense(p.du_batch_stride, p.du_d_stride) ||
-        !dense(p.ddelta_batch_stride, p.ddelta_d_stride)) return false;
-    if (p.A_d_stride != 1 && p.dim > 1) return false;
-    if (((uintptr_t)p.u | (uintptr_t)p.delta | (uintptr_t)p.dout | (uintptr_t)p.du | (uintptr_t)p.ddelta | (uintptr_t)p.B | (uintptr_t)p.C) & 7)
-        return false;
-    if (((p.B_batch_stride | p.B_group_stride | p.C_batch_stride | p.C_group_stride) * es) % 8) return false;   // 8-byte B / C pieces
-    memset(&r, 0, sizeof(r));
-    r.batch = p.batch; r.dim = p.dim; r.L = L; r.G = p.n_groups; r.rows_per_group = rpg; r.softplus = p.delta_softplus;
-    r.n_items = p.batch * p.n_groups * (rpg / 32);
-    r.nblk = (L + mia::kBlk - 1) / mia::kBlk;
-    r.nwin = (L + mia::kWinTok - 1) / mia::kWinTok;
-    // +8 bytes (2-byte types: rows stay 8-byte aligned for the 4-token quads) / +16 (fp32: 16-byte quads): shifts the rows
-    // across the shared-memory banks
-    r.pitch = mia::kWinTok * es + (es == 4 ? 16 : 8);
-    r.pitcho = mia::kWinTok * eo + (eo == 4 ? 16 : 8);
-    r.off_u = 0;
-    r.off_d = round_up(32 * r.pitch, 16);
-    r.off_o = 2 * r.off_d;
-    r.off_bcraw = r.off_o + round_up(32 * r.pitcho, 16);
-    r.stage_bytes = round_up(r.off_bcraw + 2 * mia::kWinTok * es, 128);
-    r.off_bc32 = 2 * r.stage_bytes;
-    r.smem_bytes = r.off_bc32 + 2 * mia::kWinTok * 4;
-    r.u = p.u; r.delta = p.delta; r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.dout = p.dout;
-    r.hblk = p.hblk; r.du = p.du; r.ddelta = p.ddelta;
-    r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride;
-    int per_sm = (227 * 1024) / (r.smem_bytes + 1024);
-    if (per_sm > 12) per_sm = 12;                               // 32 threads x 168 registers
-    if (per_sm < 1) return false;
-    grid = di.sms * per_sm;
-    if (grid > r.n_items) grid = r.n_items;
-    return true;
-}
-
-// Windowed row-serial backward fed by tensor-map TMA boxes (scan_bwd_wtma.cuh): eligibility, argument block, the five tensor maps
-// (u, delta, dout, du, ddelta).  Rows whose byte pitch is not a multiple of 16 are mapped two to a tensor-map row (g = 2).
-bool plan_wtma_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::WinTmaArgs &r, CUtensorMap *tm, int &grid) {
-    const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
-    const int rpg = p.dim / p.n_groups;
-    if (!p.hblk || p.dstate != 1 || p.z || p.delta_dim != p.dim || (rpg % 32) || (L % 4)) return false;
-    if (dbg_knob("MIA_NO_WTMA_BWD")) return false;
-    auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
-    if (!dense(p.u_batch_stride, p.u_d_stride) || !dense(p.delta_batch_stride, p.delta_d_stride) ||
-        !dense(p.dout_batch_stride, p.dout_d_stride) || !dense(p.du_batch_stride, p.du_d_stride) ||
-        !dense(p.ddelta_batch_stride, p.ddelta_d_stride)) return false;
-    if (p.A_d_stride != 1 && p.dim > 1) return false;
-    if (((uintptr_t)p.u | (uintptr_t)p.delta | (uintptr_t)p.dout | (uintptr_t)p.du | (uintptr_t)p.ddelta) & 15) return false;
-    if (((long long)L * es) % 16) return false;                  // rows must be tensor-map rows (else: the column-walk kernels)
-    const int g = 1;
-    const unsigned long long trows = (unsigned long long)p.batch * p.dim / g, tcols = (unsigned long long)g * L;
-    if (tcols >= (1ull << 31) || trows >= (1ull << 31)) return false;
-    memset(&r, 0, sizeof(r));
-    r.batch = p.batch; r.dim = p.dim; r.L = L; r.G = p.n_groups; r.rows_per_group = rpg; r.softplus = p.delta_softplus;
-    r.n_items = p.batch * p.n_groups * (rpg / 32);
-    r.nblk = (L + mia::kBlk - 1) / mia::kBlk;
-    r.nwin = (L + mia::kWtTok - 1) / mia::kWtTok;
-    r.g = g;
-    const int tile_i = 32 * mia::kWtTok * es, tile_o = 32 * mia::kWtTok * eo;
-    r.off_d = tile_i; r.off_o = 2 * tile_i;
-    r.in_stage = 2 * tile_i + tile_o;
-    r.out_stage = 2 * tile_i;
-    r.off_outs = 2 * r.in_stage;
-    r.off_bc32 = r.off_outs + r.out_stage;
-    r.off_bar = r.off_bc32 + 2 * mia::kWtTok * 4;
-    r.smem_bytes = r.off_bar + 16 + 1024;                        // + slack for the 1024-byte alignment of the tiles
-    r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias;
-    r.hblk = p.hblk; r.du = p.du; r.ddelta = p.ddelta;
-    r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride;
-    const void *ptrs[5] = {p.u, p.delta, p.dout, p.du, p.ddelta};
-    for (int i = 0; i < 5; ++i) {
-        const int e = i == 2 ? eo : es;
-        const int trc = mia::tma_make_2d(&tm[i], ptrs[i], trows, tcols, tcols * e, 32 / g, mia::kWtTok, e, mia::kWtTok * e);
-        if (trc != 0) { MIA_TRACE("wtma: tensor map %d rejected (CUresult %d): rows %llu cols %llu", i, trc, trows, tcols); return false; }
-    }
-    int per_sm = (227 * 1024) / (r.smem_bytes + 1024);
-    if (per_sm > 12) per_sm = 12;                               // 32 threads x 168 registers: 3 warps per scheduler
-    if (per_sm < 1) return false;
-    grid = di.sms * per_sm;
-    if (grid > r.n_items) grid = r.n_items;
-    return true;
-}
-
 // Column-walk backward (scan_bwd_cw.cuh): eligibility, argument block, tensor maps (u, delta, dout, du, ddelta).
 bool plan_cw_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::CwBwdArgs &r, CUtensorMap *tm, int &grid) {
     const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
@@ -679,7 +578,8 @@ bool plan_cw_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::CwBwdArgs &r
     r.ns = dbg_int("MIA_CW_STAGES", 4);
     r.off_bc32 = r.ns * r.stage_bytes;
     r.off_pf = r.off_bc32 + 2 * mia::kCwGrp * 4;                // two 256-byte prefetch slots (raw B, raw C, block states)
-    r.off_bar = r.off_pf + 512;
+    r.off_red = r.off_pf + 512;                                 // [32][20] fp32 scratch of the row reductions
+    r.off_bar = r.off_red + 32 * 20 * 4;
     r.smem_bytes = r.off_bar + 8 * r.ns + 16 + 1024;            // + slack for the 1024-byte alignment of the tiles
     if ((((uintptr_t)p.B | (uintptr_t)p.C) & 3) || ((p.B_batch_stride | p.B_group_stride | p.C_batch_stride | p.C_group_stride) * es) % 4) return false;
     r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.hblk = p.hblk;
@@ -691,7 +591,13 @@ bool plan_cw_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::CwBwdArgs &r
         if (trc != 0) { MIA_TRACE("cw bwd: tensor map %d rejected (CUresult %d)", i, trc); return false; }
     }
     int per_sm = (227 * 1024) / (r.smem_bytes + 1024);
-    if (per_sm > 16) per_sm = 16;
+    if (per_sm > 12) per_sm = 12;                               // 32 threads x 168 registers: 3 warps per scheduler
+    // Many short items: 8 resident warps per SM finish an item 1.8x faster than 12 do (measured, gpurun r2s / r2t, bf16,
+    // B = 148: L = 196 0.313 against 0.354 ms, L = 200 0.302 / 0.362, L = 100 0.173 / 0.193, L = 104 0.173 / 0.184), so with
+    // at least four rounds of items the extra rounds cost less than the contention.  Few long items (L = 1024, B = 32:
+    // 0.341 against 0.291 ms; L = 6400) want every slot.
+    if (r.n_items >= 4LL * 8 * di.sms && per_sm > 8) per_sm = 8;
+    per_sm = std::min(per_sm, dbg_int("MIA_CW_MAXPERSM", per_sm));
     if (per_sm < 1) return false;
     const long long slots = (long long)di.sms * per_sm;
     const long long rounds = (r.n_items + slots - 1) / slots;
@@ -880,14 +786,10 @@ int mia_ss_fwd_writes_block_states(const mia_ss_params *pp) {
     if (!pp || !pp->hblk || validate_sizes(*pp) != MIA_OK || !pp->u || !pp->delta || !pp->out) return 0;
     DeviceInfo di;
     if (device_info(di) != MIA_OK) return 0;
-    mia::ChunkArgs rc;
-    mia::RowsArgs rr;
     mia::CwFwdArgs rw;
     CUtensorMap tm[3];
-    int grid = 0, g = 0;
-    if (plan_cw_fwd(*pp, di, rw, tm, grid)) return 1;
-    if (cw_geometry(*pp, g) && g == 2) return 0;                 // that layout is the column-walk kernels' alone
-    return (plan_chunks_fwd(*pp, di, rc, grid) || plan_rows_fwd(*pp, di, rr, grid)) ? 1 : 0;   // the other two kernels that fill hblk
+    int grid = 0;
+    return plan_cw_fwd(*pp, di, rw, tm, grid) ? 1 : 0;          // the column-walk forward is the kernel that fills hblk
 }
 
 int mia_selective_scan_fwd(const mia_ss_params *pp, void *cuda_stream) {
@@ -1037,20 +939,15 @@ int mia_selective_scan_bwd(const mia_ss_params *pp, void *cuda_stream) {
     }
     int rc = 0, bc_parts = pl.split;
     mia::RowsBwdArgs rb;
-    mia::WinBwdArgs wb;
     int rgrid = 0;
-    mia::WinTmaArgs wt;
     CUtensorMap tmaps[5];
-    int cwg = 0;
-    const bool hblk_std = p.hblk && !(cw_geometry(p, cwg) && cwg == 2);      // block states in the token-aligned layout
-    // Windowed kernels (one warp per 32 rows, phase 2 only): rows of more than one 256-token chunk, and enough 32-row items to
-    // fill the SMs.  Measured (gpurun r2i, L = 6400, bf16): B = 16 (1536 items) 1.16 ms against 1.76 ms for the warp-scan
-    // kernel; B = 4 (384 items = 2.6 warps per SM) 0.75 ms against 0.55 ms.
+    // Column-walk kernel (one warp per 32 g rows, phase 2 only, on the forward's block states): short rows always; rows of more
+    // than one 256-token chunk only with enough 32-row items to fill the SMs.  Measured (gpurun r2i / r2n, L = 6400, bf16):
+    // B = 16 (1536 items) 0.86 ms against 1.77 ms for the warp-scan kernel; B = 4 (384 items = 2.6 warps per SM): a one-warp-
+    // per-item walk took 0.75 ms against 0.55 ms.
     const long long items32 = (long long)p.batch * (p.dim / 32);
-    const bool want_win = !use_rowsn && hblk_std &&
-                          ((p.seqlen > mia::kRowsChunk && items32 >= 4LL * di.sms) || dbg_knob("MIA_FORCE_WIN_BWD"));
     mia::CwBwdArgs cwb;
-    const bool want_cw = !use_rowsn && p.hblk && (items32 >= 4LL * di.sms || dbg_knob("MIA_FORCE_CW_BWD"));
+    const bool want_cw = !use_rowsn && p.hblk && (p.seqlen <= mia::kRowsChunk || items32 >= 4LL * di.sms || dbg_knob("MIA_FORCE_CW_BWD"));
     if (want_cw && plan_cw_bwd(p, di, cwb, tmaps, rgrid)) {
         MIA_TRACE("bwd: cw g=%d ns=%d ngrp=%d grid=%d smem=%d", cwb.g, cwb.ns, cwb.ngrp, rgrid, cwb.smem_bytes);
         cwb.part_dA = a.part_dA; cwb.part_dD = a.part_dD; cwb.part_dbias = a.part_dbias; cwb.acc_dB = a.acc_dB; cwb.acc_dC = a.acc_dC;
@@ -1059,24 +956,6 @@ int mia_selective_scan_bwd(const mia_ss_params *pp, void *cuda_stream) {
         rc = dispatch(p.itype, [&](auto *tag) {
             using T = typename std::remove_pointer<decltype(tag)>::type;
             return (int)mia::launch_bwd_cw<T>(tmaps, cwb, rgrid, of32, stream);
-        });
-    } else if (want_win && dbg_knob("MIA_WTMA_BWD") && plan_wtma_bwd(p, di, wt, tmaps, rgrid)) {
-        MIA_TRACE("bwd: wtma g=%d nwin=%d grid=%d smem=%d", wt.g, wt.nwin, rgrid, wt.smem_bytes);
-        wt.part_dA = a.part_dA; wt.part_dD = a.part_dD; wt.part_dbias = a.part_dbias; wt.acc_dB = a.acc_dB; wt.acc_dC = a.acc_dC;
-        bc_parts = wt.rows_per_group / 32;
-        const bool of32 = p.otype == MIA_F32 && p.itype != MIA_F32;
-        rc = dispatch(p.itype, [&](auto *tag) {
-            using T = typename std::remove_pointer<decltype(tag)>::type;
-            return (int)mia::launch_bwd_wtma<T>(tmaps, wt, rgrid, of32, stream);
-        });
-    } else if (want_win && plan_win_bwd(p, di, wb, rgrid)) {
-        MIA_TRACE("bwd: win (cp.async) nwin=%d grid=%d", wb.nwin, rgrid);
-        wb.part_dA = a.part_dA; wb.part_dD = a.part_dD; wb.part_dbias = a.part_dbias; wb.acc_dB = a.acc_dB; wb.acc_dC = a.acc_dC;
-        bc_parts = wb.rows_per_group / 32;
-        const bool of32 = p.otype == MIA_F32 && p.itype != MIA_F32;
-        rc = dispatch(p.itype, [&](auto *tag) {
-            using T = typename std::remove_pointer<decltype(tag)>::type;
-            return (int)mia::launch_bwd_win<T>(wb, rgrid, of32, stream);
         });
     } else if (use_rowsn) {
         rn.part_dA = a.part_dA; rn.part_dD = a.part_dD; rn.part_dbias = a.part_dbias; rn.acc_dB = a.acc_dB; rn.acc_dC = a.acc_dC;

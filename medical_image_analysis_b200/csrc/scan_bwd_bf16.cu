@@ -2,14 +2,10 @@
 #include "scan_bwd_fast.cuh"
 #include "scan_bwd_rows.cuh"
 #include "scan_bwd_rowsn.cuh"
-#include "scan_bwd_win.cuh"
-#include "scan_bwd_wtma.cuh"
 #include "scan_bwd_cw.cuh"
 namespace mia {
 template cudaError_t launch_bwd_any<__nv_bfloat16>(const ScanArgs &, int, cudaStream_t);
 template cudaError_t launch_bwd_rows<__nv_bfloat16>(const RowsBwdArgs &, int, bool, cudaStream_t);
 template cudaError_t launch_bwd_rowsn<__nv_bfloat16>(const RowsNBwdArgs &, int, bool, cudaStream_t);
-template cudaError_t launch_bwd_win<__nv_bfloat16>(const WinBwdArgs &, int, bool, cudaStream_t);
 template cudaError_t launch_bwd_cw<__nv_bfloat16>(const CUtensorMap *, const CwBwdArgs &, int, bool, cudaStream_t);
-template cudaError_t launch_bwd_wtma<__nv_bfloat16>(const CUtensorMap *, const WinTmaArgs &, int, bool, cudaStream_t);
 }  // namespace mia

@@ -34,7 +34,7 @@ struct CwBwdArgs {
     int batch, dim, L, G, rows_per_group;
     int softplus;
     int g, n_items, ngrp, ns;               // rows per tensor-map row; items of 32 g rows; 16-column groups per tensor-map row; stages
-    int stage_bytes, off_bc32, off_pf, off_bar, smem_bytes;
+    int stage_bytes, off_bc32, off_pf, off_red, off_bar, smem_bytes;
     const void *A, *B, *C, *D, *delta_bias;
     const float *hblk;
     float *part_dA, *part_dD, *part_dbias, *acc_dB, *acc_dC;
@@ -59,28 +59,35 @@ struct CwRegs {
     float2 a[8], hp[8], m[8];      // a_t, a_t h_{t-1}, softplus(delta + bias) log2e of the 16 tokens
 };
 
-// Sum each of 16 per-lane values over the 32 lanes: transposing butterfly (strides 8, 4, 2, 1: a lane keeps the half of its
-// values whose index has that bit equal to its own lane bit, summed with the partner's copy), then the two 16-lane halves are
-// added.  16 shuffles; lane i ends with the warp total of v[i & 15] in v[0].
-__device__ __forceinline__ void butterfly16(float (&v)[16], const int lane) {
+// Sum each of 16 per-lane values over the 32 lanes through shared memory: every lane writes its 16 values as one row of a
+// [32][20] fp32 scratch (80-byte pitch: the four 16-byte stores of 8 lanes fall into 8 different 16-byte slots), then lane l
+// adds value l % 16 over the 16 lanes of its half (column reads; the upper half starts 4 rows further so that the two halves
+// use disjoint banks), and one shuffle adds the halves.  4 STS.128 + 16 LDS + 16 FADD + 1 SHFL against 16 SHFL + 16 FADD +
+// 30 FSEL for a transposing butterfly; fixed summation order.  Returns the warp total of v[l % 16].
+__device__ __forceinline__ float reduce16(const float (&v)[16], const int lane, float *red) {
+    float4 *row = reinterpret_cast<float4 *>(red + lane * 20);
 #pragma unroll
-    for (int s = 8; s >= 1; s >>= 1) {
-        const bool up = (lane & s) != 0;
+    for (int i = 0; i < 4; ++i) row[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    __syncwarp();
+    const int half = lane >> 4;
+    const float *col = red + half * 16 * 20 + (lane & 15);
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < s; ++i) {
-            const float send = up ? v[i] : v[i + s];
-            const float keep = up ? v[i + s] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-        }
+    for (int k = 0; k < 16; k += 2) {
+        s0 += col[((k + 4 * half) & 15) * 20];
+        s1 += col[((k + 1 + 4 * half) & 15) * 20];
     }
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+    __syncwarp();                                                        // the scratch is rewritten by the next reduction
+    float s = s0 + s1;
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
+    return s;
 }
 
 // One group (or the part of it that belongs to one row): quads [qlo, qhi) of the 16 columns.  tok0: token of the group's
 // first column in the current row (negative for the odd row's head); h0: state entering quad qlo.
 template <typename T, typename TO, bool kSoftplus, bool kFull>
 __device__ __forceinline__ void cw_bwd_block(const int qlo_in, const int qhi_in, const int tok0, const int lane, const float h0, char *tu, char *td,
-                                             const char *to, const SwzRow ri, const SwzRow ro, const float *Bf, const float *Cf, float *accB,
+                                             const char *to, const SwzRow ri, const SwzRow ro, const float *Bf, const float *Cf, float *red, float *accB,
                                              float *accC, const float2 bl2, const float2 A2, const float2 Aln2, const float2 D2, float &G,
                                              float2 &dA2, float2 &dD2, float2 &db2) {
     constexpr int es = (int)sizeof(T), eo = (int)sizeof(TO);
@@ -122,8 +129,8 @@ __device__ __forceinline__ void cw_bwd_block(const int qlo_in, const int qhi_in,
             }
         }
     }
-    butterfly16(v, lane);
-    if (mine && lane < 16) accC[tok0 + i16] = v[0];
+    const float dCt = reduce16(v, lane, red);
+    if (mine && lane < 16) accC[tok0 + i16] = dCt;
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = 0.f;
     // ---- suffix recurrence G_t = a_t (dy_t C_t + G_{t+1}), gradients of the block
@@ -158,8 +165,8 @@ __device__ __forceinline__ void cw_bwd_block(const int qlo_in, const int qhi_in,
             Quad<T>::st(td + ri.at(4 * q * es), dd);
         }
     }
-    butterfly16(v, lane);
-    if (mine && lane < 16) accB[tok0 + i16] = v[0] * kLn2;
+    const float dBt = reduce16(v, lane, red);
+    if (mine && lane < 16) accB[tok0 + i16] = dBt * kLn2;
 }
 
 template <typename T, bool kSoftplus, bool kOutF32, int kG>
@@ -228,6 +235,7 @@ __global__ void __launch_bounds__(32, 12) ss_bwd_cw_kernel(const __grid_constant
     // for the load -- measured: the dominant stall of the first version).  Slot: [raw B 64 B][raw C 64 B][32 block states].
     constexpr int kEpw = 4 / es, kNw = kCwGrp / kEpw;                    // elements per 4-byte word, words per 16 columns
     char *pf = smem + a.off_pf;
+    float *red = reinterpret_cast<float *>(smem + a.off_red);
     const raw *gBC = nullptr;                                            // this lane's B or C row of the item the prefetch is in
     const float *gh = nullptr;
     auto bc_rows = [&](int item) {
@@ -313,7 +321,7 @@ __global__ void __launch_bounds__(32, 12) ss_bwd_cw_kernel(const __grid_constant
             const bool split = kG == 2 && cb < L && cb + kCwGrp > L;     // the group holds the end of the even row and the start of the odd one
             if (!split && qend == 4) {
                 const int tok0 = cb - seg * L;
-                cw_bwd_block<T, TO, kSoftplus, true>(0, 4, tok0, lane, tok0 == 0 ? 0.f : hslot, tu, td, to, ri, ro, Bw, Cw, accB, accC, bl2, A2, Aln2,
+                cw_bwd_block<T, TO, kSoftplus, true>(0, 4, tok0, lane, tok0 == 0 ? 0.f : hslot, tu, td, to, ri, ro, Bw, Cw, red, accB, accC, bl2, A2, Aln2,
                                                      D2, G, dA2, dD2, db2);
             } else {
                 // partial group (end of the tensor-map row), or the split group: quads [qe, qend) are the head of the odd row
@@ -336,7 +344,7 @@ __global__ void __launch_bounds__(32, 12) ss_bwd_cw_kernel(const __grid_constant
                     } else {
                         qlo = 0; qhi = qend; tok0 = cb - seg * L; h0 = tok0 == 0 ? 0.f : hslot;
                     }
-                    cw_bwd_block<T, TO, kSoftplus, false>(qlo, qhi, tok0, lane, h0, tu, td, to, ri, ro, Bw, Cw, accB, accC, bl2, A2, Aln2, D2, G, dA2,
+                    cw_bwd_block<T, TO, kSoftplus, false>(qlo, qhi, tok0, lane, h0, tu, td, to, ri, ro, Bw, Cw, red, accB, accC, bl2, A2, Aln2, D2, G, dA2,
                                                           dD2, db2);
                 }
             }

@@ -2,14 +2,10 @@
 #include "scan_bwd_fast.cuh"
 #include "scan_bwd_rows.cuh"
 #include "scan_bwd_rowsn.cuh"
-#include "scan_bwd_win.cuh"
-#include "scan_bwd_wtma.cuh"
 #include "scan_bwd_cw.cuh"
 namespace mia {
 template cudaError_t launch_bwd_any<__half>(const ScanArgs &, int, cudaStream_t);
 template cudaError_t launch_bwd_rows<__half>(const RowsBwdArgs &, int, bool, cudaStream_t);
 template cudaError_t launch_bwd_rowsn<__half>(const RowsNBwdArgs &, int, bool, cudaStream_t);
-template cudaError_t launch_bwd_win<__half>(const WinBwdArgs &, int, bool, cudaStream_t);
 template cudaError_t launch_bwd_cw<__half>(const CUtensorMap *, const CwBwdArgs &, int, bool, cudaStream_t);
-template cudaError_t launch_bwd_wtma<__half>(const CUtensorMap *, const WinTmaArgs &, int, bool, cudaStream_t);
 }  // namespace mia

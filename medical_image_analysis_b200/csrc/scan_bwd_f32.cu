@@ -2,14 +2,10 @@
 #include "scan_bwd_fast.cuh"
 #include "scan_bwd_rows.cuh"
 #include "scan_bwd_rowsn.cuh"
-#include "scan_bwd_win.cuh"
-#include "scan_bwd_wtma.cuh"
 #include "scan_bwd_cw.cuh"
 namespace mia {
 template cudaError_t launch_bwd_any<float>(const ScanArgs &, int, cudaStream_t);
 template cudaError_t launch_bwd_rows<float>(const RowsBwdArgs &, int, bool, cudaStream_t);
 template cudaError_t launch_bwd_rowsn<float>(const RowsNBwdArgs &, int, bool, cudaStream_t);
-template cudaError_t launch_bwd_win<float>(const WinBwdArgs &, int, bool, cudaStream_t);
 template cudaError_t launch_bwd_cw<float>(const CUtensorMap *, const CwBwdArgs &, int, bool, cudaStream_t);
-template cudaError_t launch_bwd_wtma<float>(const CUtensorMap *, const WinTmaArgs &, int, bool, cudaStream_t);
 }  // namespace mia

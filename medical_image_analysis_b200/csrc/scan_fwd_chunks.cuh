@@ -29,8 +29,6 @@ struct ChunkArgs {
     const void *u, *delta, *A, *B, *C, *D, *delta_bias;
     void *out;
     float *x;
-    float *hblk;                           // optional [32-row batch][nblk16][32] block-entering states (pass C writes them)
-    int nblk16;
     long long B_bs, B_gs, C_bs, C_gs;
 };
 
@@ -124,8 +122,6 @@ __global__ void __launch_bounds__(32) ss_fwd_chunk_kernel(const __grid_constant_
             if (!kStateOnly) {
                 if (kOutF32) *reinterpret_cast<float4 *>(orow + (size_t)t * 4) = make_float4(y[0].x, y[0].y, y[1].x, y[1].y);
                 else Quad<T>::st(pu + t * es, y);            // y replaces u in place
-                if (a.hblk && ((l0 + t + 4) & 15) == 0 && l0 + t + 4 < L)
-                    a.hblk[((size_t)rb * a.nblk16 + ((l0 + t + 4) >> 4)) * 32 + lane] = h;
             }
         }
         if (kStateOnly) {

@@ -30,8 +30,6 @@ struct RowsArgs {
     const void *u, *delta, *A, *B, *C, *D, *delta_bias;
     void *out;
     float *x;
-    float *hblk;                         // optional [item][nblk16][32]: state entering every 16-token block (for scan_bwd_win.cuh)
-    int nblk16;
     long long B_bs, B_gs, C_bs, C_gs;    // element strides of B / C (sequence stride is 1, d_state == 1)
 };
 
@@ -114,7 +112,6 @@ __global__ void __launch_bounds__(32) ss_fwd_rows_kernel(const __grid_constant__
         float2 msum = make_float2(0.f, 0.f);     // sum of softplus * log2e so far (prod a = 2^(A * sum))
         float2 *xrow = reinterpret_cast<float2 *>(a.x) + ((size_t)b * a.dim + d) * a.xchunks;
         int xc = 0, to_ck = min(a.xchunk_tokens, L);   // next checkpoint slot, tokens until it is due
-        float *hb = a.hblk ? a.hblk + (size_t)item * a.nblk16 * 32 + lane : nullptr;
         for (int c = 0; c < nch; ++c) {
             const int l0 = c * Lc, len = min(Lc, L - l0);
             // ---- stage: u / delta tiles by TMA (one flat 32-row span when the chunk is the whole row, else one piece per
@@ -174,8 +171,6 @@ __global__ void __launch_bounds__(32) ss_fwd_rows_kernel(const __grid_constant__
                     }
                     if (kOutF32) *reinterpret_cast<float4 *>(orow + (size_t)t * 4) = make_float4(y[0].x, y[0].y, y[1].x, y[1].y);
                     else Quad<T>::st(pu + t * es, y);            // y replaces u in place
-                    // state entering the next 16-token block (coalesced: 32 lanes x 4 bytes per block)
-                    if (hb && ((l0 + t + 4) & 15) == 0 && l0 + t + 4 < L) hb[((l0 + t + 4) >> 4) * 32] = h;
                 }
                 t0 += nt;
                 to_ck -= nt;

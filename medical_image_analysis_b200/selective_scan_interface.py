@@ -30,7 +30,7 @@ class SelectiveScanOflex(torch.autograd.Function):
     def forward(ctx, u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1, backnrows=1, oflex=True):
         ctx.delta_softplus = delta_softplus
         out, x, *rest = selective_scan_cuda_oflex.fwd(u, delta, A, B, C, D, delta_bias, delta_softplus, 1, oflex)
-        ctx.has_hblk = len(rest) > 0                       # block states for the windowed backward (scan_bwd_win.cuh)
+        ctx.has_hblk = len(rest) > 0                       # block states for the column-walk backward (scan_bwd_cw.cuh)
         ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, x, *rest[:1])
         return out
 
@@ -53,7 +53,7 @@ class SelectiveScanCore(torch.autograd.Function):
     def forward(ctx, u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1, backnrows=1, oflex=True):
         ctx.delta_softplus = delta_softplus
         out, x, *rest = selective_scan_cuda_core.fwd(u, delta, A, B, C, D, delta_bias, delta_softplus, 1)
-        ctx.has_hblk = len(rest) > 0                       # block states for the windowed backward (scan_bwd_win.cuh)
+        ctx.has_hblk = len(rest) > 0                       # block states for the column-walk backward (scan_bwd_cw.cuh)
         ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, x, *rest[:1])
         return out
 

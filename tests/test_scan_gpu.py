@@ -66,7 +66,7 @@ def _run_case(batch, dim, L, N, G, ddim, has_D, has_z, has_bias, softplus, dtype
     # inherits that rounding (half an ulp) on top of its own -> 2 ulp for dz in that configuration only
     dz_ulp = 2.0 if (has_z and lowp and not out_float) else 1.0
     # both backward families: without the forward's block states (resident-row / warp-scan kernels) and, where the forward
-    # produced them (d_state 1 row-serial shapes), with them (windowed kernel, scan_bwd_win.cuh)
+    # produced them (d_state 1 row-serial shapes), with them (column-walk kernel, scan_bwd_cw.cuh)
     for path, hb in (("", None),) + ((("[hblk]", hblk),) if hblk is not None else ()):
         du, dd, dA, dB, dC, dD, dbias, dz = scan_bwd(gpu["u"], gpu["delta"], gpu["A"], gpu["B"], gpu["C"], gpu["D"], gpu["z"],
                                                      gpu["delta_bias"], dout, x, out if has_z else None, softplus, hblk=hb)
@@ -228,8 +228,8 @@ def test_scan_m196_shape(N, out_float):
 
 
 # Every bench.py WORKLOADS geometry at a reduced batch (What's weak 1): the kernels bench.py times are the
-# kernels checked here -- L = 6400 takes the 25-chunk row-serial backward + the 3-launch chunk-parallel forward at
-# d_state 1 and the warp-scan kernels over 25 chunks at d_state 16; (R=768, L=197, z) is one scan of the ARM mixer.
+# kernels checked here -- at these small batches L = 6400 takes the 3-launch chunk-parallel forward and the warp-scan backward
+# (the column-walk kernels of the full batch: test_scan_headline_batches_spot_images); (R=768, L=197, z) is one scan of the ARM mixer.
 @pytest.mark.parametrize("N", [1, 16])
 @pytest.mark.parametrize("batch", [1, 2])
 def test_scan_m6400_shape(N, batch):
@@ -246,27 +246,32 @@ def test_scan_arm_mixer_shape(dtype, out_float):
     _run_case(2, 768, 197, 16, 1, 768, True, True, True, True, dtype, out_float, seed=23)
 
 
-def test_scan_m196_full_wave_batch_spot_rows():
-    """B = 148 (the headline batch: full waves of the forward's resident warps) checked on a few images: the oracle runs
-    on images {0, 73, 147} only, the CUDA path on the whole batch (identical inputs for those images)."""
+@pytest.mark.parametrize("B,L,imgs", [(148, 196, (0, 73, 147)), (16, 6400, (0, 9, 15))], ids=["m196_B148", "m6400_B16"])
+def test_scan_headline_batches_spot_images(B, L, imgs):
+    """bench.py's two headline workloads at their FULL per-GPU batch (the kernels and grids the bench times: column-walk forward
+    and backward, two rows per tensor-map row at L = 196): the oracle runs on three images only, the CUDA path on the whole
+    batch (identical inputs for those images).  fp32 criteria scale with L / 256 like everywhere (parity.long_row_scale)."""
     from medical_image_analysis_b200 import scan_bwd, scan_fwd
     from oracle import ss_ref_c
-    from tests.parity import cmp_auto
-    B, R, G, L, N = 148, 3072, 4, 196, 1
+    from tests.parity import cmp_auto, long_row_scale
+    R, G, N = 3072, 4, 1
+    fs = long_row_scale(L)
     cpu, gpu = _inputs(31, B, R, L, N, G, R, True, False, True, torch.bfloat16)
     out, x, _, hblk = scan_fwd(gpu["u"], gpu["delta"], gpu["A"], gpu["B"], gpu["C"], gpu["D"], None, gpu["delta_bias"], True, False,
                                want_block_states=True)
-    assert hblk is not None                                      # bench.py's path: the windowed backward on the forward's block states
+    assert hblk is not None                                      # bench.py's path: the column-walk backward on the forward's block states
     grads = scan_bwd(gpu["u"], gpu["delta"], gpu["A"], gpu["B"], gpu["C"], gpu["D"], None, gpu["delta_bias"], gpu["dout"], x, None, True,
                      hblk=hblk)
-    for b in (0, 73, 147):
+    for b in imgs:
         sl = {k: (v[b:b + 1] if (v is not None and v.dim() >= 3) else v) for k, v in cpu.items()}
         r_out, _, r_last = ss_ref_c.fwd(sl["u"], sl["delta"], sl["A"], sl["B"], sl["C"], sl["D"], None, sl["delta_bias"], True)
-        cmp_auto(out[b:b + 1], r_out, f"B148 img{b} out")
-        cmp_auto(x[b:b + 1, :, -1, 1::2], r_last, f"B148 img{b} last_state")
+        cmp_auto(out[b:b + 1], r_out, f"B{B} L{L} img{b} out", f32_scale=fs)
+        cmp_auto(x[b:b + 1, :, -1, 1::2], r_last, f"B{B} L{L} img{b} last_state", f32_scale=fs)
         ref = ss_ref_c.bwd(sl["u"], sl["delta"], sl["A"], sl["B"], sl["C"], sl["D"], None, sl["delta_bias"], sl["dout"], True)
+        # L = 6400: 2 of 19.66 M du elements of image 0 sit 2 bf16 ulp from the rounded oracle (measured, gpurun r2o: 1.23 x the
+        # 1-ulp criterion; 25 chunks of fp32 recurrence in front of the rounding) -> 2 ulp for rows of more than one chunk
         for name, idx in (("du", 0), ("ddelta", 1), ("dB", 3), ("dC", 4)):      # per-image gradients
-            cmp_auto(grads[idx][b:b + 1], ref[name], f"B148 img{b} {name}")
+            cmp_auto(grads[idx][b:b + 1], ref[name], f"B{B} L{L} img{b} {name}", n_ulp=1.0 if L <= 256 else 2.0, f32_scale=fs)
 
 
 def test_scan_strided_inputs():
@@ -283,12 +288,11 @@ def test_scan_strided_inputs():
     _cmp(out, r_out, 1e-5, 2e-5 * max(1.0, r_out.abs().max().item()), "out")
 
 
-@pytest.mark.parametrize("shape", [(4, 128, 304, 2), (10, 2048, 196, 2), (19, 1024, 288, 1)], ids=lambda s: f"b{s[0]}d{s[1]}L{s[2]}G{s[3]}")
+@pytest.mark.parametrize("shape", [(4, 128, 196, 2), (10, 2048, 196, 2), (19, 1024, 288, 1)], ids=lambda s: f"b{s[0]}d{s[1]}L{s[2]}G{s[3]}")
 @pytest.mark.parametrize("use_hblk", [False, True])
 def test_bwd_is_deterministic_dstate1(shape, use_hblk):
     """Bit-identical gradients from two runs: resident-row / warp-scan kernels (no block states) and the kernels that consume
-    the forward's block states (windowed kernel on the small shape, column-walk kernel -- one and two rows per tensor-map row --
-    on the two large ones)."""
+    the forward's block states (column-walk kernel, one and two rows per tensor-map row)."""
     from medical_image_analysis_b200 import scan_bwd, scan_fwd
     batch, dim, L, G = shape
     _, g = _inputs(9, batch, dim, L, 1, G, dim, True, False, True, torch.bfloat16)

@@ -29,13 +29,12 @@ def build_debug():
 
 VARIANTS = {
     "default": {},
-    "cw_forced": {"MIA_FORCE_CW_BWD": "1"},
-    "cw_3stages": {"MIA_FORCE_CW_BWD": "1", "MIA_CW_STAGES": "3"},
-    "cw_6stages": {"MIA_FORCE_CW_BWD": "1", "MIA_CW_STAGES": "6"},
     "no_cw": {"MIA_NO_CW_BWD": "1"},
-    "win_cpasync": {"MIA_NO_CW_BWD": "1", "MIA_FORCE_WIN_BWD": "1"},
     "no_hblk": None,          # backward without block states: resident-row / warp-scan kernels
 }
+for _ns in (3, 4, 6, 8):
+    for _cap in (6, 8, 10, 12):
+        VARIANTS[f"cw_ns{_ns}_cap{_cap}"] = {"MIA_FORCE_CW_BWD": "1", "MIA_CW_STAGES": str(_ns), "MIA_CW_MAXPERSM": str(_cap)}
 
 
 def main():
@@ -64,9 +63,12 @@ def main():
         bias = 0.5 * torch.rand(D, device="cuda", generator=g)
         dout = torch.randn(B, D, L, device="cuda", generator=g).to(torch.float32 if of32 else dt)
         fbase = None
-        for name, env in (("fwd_default", {}), ("fwd_no_cw", {"MIA_NO_CW_FWD": "1"}), ("fwd_cw_3stages", {"MIA_CW_STAGES": "3"}),
-                          ("fwd_cw_4stages", {"MIA_CW_STAGES": "4"}), ("fwd_cw_forced", {"MIA_FORCE_CW_FWD": "1"})):
-            for k in ("MIA_NO_CW_FWD", "MIA_CW_STAGES", "MIA_FORCE_CW_FWD"):
+        fvars = [("fwd_default", {}), ("fwd_no_cw", {"MIA_NO_CW_FWD": "1"})]
+        for _ns in (3, 4):
+            for _cap in (6, 8, 10, 12, 16):
+                fvars.append((f"fwd_cw_ns{_ns}_cap{_cap}", {"MIA_CW_STAGES": str(_ns), "MIA_CW_MAXPERSM": str(_cap)}))
+        for name, env in fvars:
+            for k in ("MIA_NO_CW_FWD", "MIA_CW_STAGES", "MIA_FORCE_CW_FWD", "MIA_CW_MAXPERSM"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             runf = lambda: scan_fwd(u, delta, A, Bm, Cm, Dv, None, bias, True, of32, want_block_states=True)
@@ -89,12 +91,12 @@ def main():
             byt = B * D * L * (u.element_size() * 2 + res[0].element_size())
             print(json.dumps({"B": B, "L": L, "dtype": str(dt), "of32": of32, "variant": name, "ms": round(ms, 4),
                               "GBps": round(byt / ms / 1e6, 1), "max_abs_diff_vs_default": diff, "hblk": res[3] is not None}), flush=True)
-        for k in ("MIA_NO_CW_FWD", "MIA_CW_STAGES", "MIA_FORCE_CW_FWD"):
+        for k in ("MIA_NO_CW_FWD", "MIA_CW_STAGES", "MIA_FORCE_CW_FWD", "MIA_CW_MAXPERSM"):
             os.environ.pop(k, None)
         out, x, _, hblk = scan_fwd(u, delta, A, Bm, Cm, Dv, None, bias, True, of32, want_block_states=True)
         base = None
         for name, env in VARIANTS.items():
-            for k in ("MIA_FORCE_WIN_BWD", "MIA_NO_WTMA_BWD", "MIA_NO_WIN_BWD", "MIA_FORCE_CW_BWD", "MIA_NO_CW_BWD", "MIA_CW_STAGES"):
+            for k in ("MIA_FORCE_WIN_BWD", "MIA_NO_WTMA_BWD", "MIA_NO_WIN_BWD", "MIA_FORCE_CW_BWD", "MIA_NO_CW_BWD", "MIA_CW_STAGES", "MIA_CW_MAXPERSM"):
                 os.environ.pop(k, None)
             if env:
                 os.environ.update(env)
