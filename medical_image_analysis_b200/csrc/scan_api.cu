@@ -573,21 +573,25 @@ bool plan_cw_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::CwBwdArgs &r
     r.g = g;
     r.n_items = p.batch * p.n_groups * (rpg / (32 * g));
     r.ngrp = (g * L + mia::kCwGrp - 1) / mia::kCwGrp;
-    const int tile_i = 32 * mia::kCwGrp * es, tile_o = 32 * mia::kCwGrp * eo;
+    r.nwin = (g * L + mia::kCwWin - 1) / mia::kCwWin;
+    const int tile_i = 32 * mia::kCwWin * es, tile_o = 32 * mia::kCwWin * eo;
     r.stage_bytes = 2 * tile_i + tile_o;
-    r.ns = dbg_int("MIA_CW_STAGES", 4);
+    // Many short items want 8 resident warps per SM (see below) and can afford 3 stages; otherwise 2 stages (one 32-column window
+    // of lead = the 2-group lead of the 16-column ring measured best on long rows) so that 12 warps per SM fit
+    const bool many_short = r.n_items >= 4LL * 8 * di.sms;
+    r.ns = dbg_int("MIA_CW_STAGES", many_short ? 3 : 2);
     r.off_bc32 = r.ns * r.stage_bytes;
-    r.off_pf = r.off_bc32 + 2 * mia::kCwGrp * 4;                // two 256-byte prefetch slots (raw B, raw C, block states)
-    r.off_red = r.off_pf + 512;                                 // [32][20] fp32 scratch of the row reductions
+    r.off_pf = r.off_bc32 + 2 * mia::kCwWin * 4;                // two 512-byte prefetch slots (raw B, raw C, block states of 2 groups)
+    r.off_red = r.off_pf + 1024;                                // [32][20] fp32 scratch of the row reductions
     r.off_bar = r.off_red + 32 * 20 * 4;
-    r.smem_bytes = r.off_bar + 8 * r.ns + 16 + 1024;            // + slack for the 1024-byte alignment of the tiles
+    r.smem_bytes = r.off_bar + 8 * r.ns + 16;
     if ((((uintptr_t)p.B | (uintptr_t)p.C) & 3) || ((p.B_batch_stride | p.B_group_stride | p.C_batch_stride | p.C_group_stride) * es) % 4) return false;
     r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.hblk = p.hblk;
     r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride;
     const void *ptrs[5] = {p.u, p.delta, p.dout, p.du, p.ddelta};
     for (int i = 0; i < 5; ++i) {
         const int e = i == 2 ? eo : es;
-        const int trc = mia::tma_make_2d(&tm[i], ptrs[i], trows, tcols, tcols * e, 32, mia::kCwGrp, e, mia::kCwGrp * e);
+        const int trc = mia::tma_make_2d(&tm[i], ptrs[i], trows, tcols, tcols * e, 32, mia::kCwWin, e, mia::kCwWin * e);
         if (trc != 0) { MIA_TRACE("cw bwd: tensor map %d rejected (CUresult %d)", i, trc); return false; }
     }
     int per_sm = (227 * 1024) / (r.smem_bytes + 1024);
@@ -596,7 +600,7 @@ bool plan_cw_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::CwBwdArgs &r
     // B = 148: L = 196 0.313 against 0.354 ms, L = 200 0.302 / 0.362, L = 100 0.173 / 0.193, L = 104 0.173 / 0.184), so with
     // at least four rounds of items the extra rounds cost less than the contention.  Few long items (L = 1024, B = 32:
     // 0.341 against 0.291 ms; L = 6400) want every slot.
-    if (r.n_items >= 4LL * 8 * di.sms && per_sm > 8) per_sm = 8;
+    if (many_short && per_sm > 8) per_sm = 8;
     per_sm = std::min(per_sm, dbg_int("MIA_CW_MAXPERSM", per_sm));
     if (per_sm < 1) return false;
     const long long slots = (long long)di.sms * per_sm;

@@ -29,31 +29,18 @@
 namespace mia {
 
 constexpr int kCwGrp = 16;       // columns per group = tokens per recompute block
+constexpr int kCwWin = 32;       // columns per window = per stage of the ring (two groups)
 
 struct CwBwdArgs {
     int batch, dim, L, G, rows_per_group;
     int softplus;
-    int g, n_items, ngrp, ns;               // rows per tensor-map row; items of 32 g rows; 16-column groups per tensor-map row; stages
+    int g, n_items, ngrp, nwin, ns;         // rows per tensor-map row; items of 32 g rows; 16-column groups / 32-column windows per tensor-map row; stages
     int stage_bytes, off_bc32, off_pf, off_red, off_bar, smem_bytes;
     const void *A, *B, *C, *D, *delta_bias;
     const float *hblk;
     float *part_dA, *part_dD, *part_dbias, *acc_dB, *acc_dC;
     long long B_bs, B_gs, C_bs, C_gs;
 };
-
-// tile rows of 32 bytes (16 two-byte columns): CU_TENSOR_MAP_SWIZZLE_32B (16-byte chunk index ^= address bit 7)
-template <int RB>
-__device__ __forceinline__ SwzRow swz_row_any(int row) {
-    if constexpr (RB == 32) {
-        const uint32_t off = (uint32_t)(row * 32);
-        SwzRow r;
-        r.line = off & ~127u;
-        r.y = (off & 127u) ^ (((off >> 7) & 1u) << 4);
-        return r;
-    } else {
-        return swz_row<RB>(row);
-    }
-}
 
 struct CwRegs {
     float2 a[8], hp[8], m[8];      // a_t, a_t h_{t-1}, softplus(delta + bias) log2e of the 16 tokens
@@ -87,8 +74,8 @@ __device__ __forceinline__ float reduce16(const float (&v)[16], const int lane, 
 // first column in the current row (negative for the odd row's head); h0: state entering quad qlo.
 template <typename T, typename TO, bool kSoftplus, bool kFull>
 __device__ __forceinline__ void cw_bwd_block(const int qlo_in, const int qhi_in, const int tok0, const int lane, const float h0, char *tu, char *td,
-                                             const char *to, const SwzRow ri, const SwzRow ro, const float *Bf, const float *Cf, float *red, float *accB,
-                                             float *accC, const float2 bl2, const float2 A2, const float2 Aln2, const float2 D2, float &G,
+                                             const char *to, const SwzRow ri, const SwzRow ro, const int wbi, const int wbo, const float *Bf, const float *Cf,
+                                             float *red, float *accB, float *accC, const float2 bl2, const float2 A2, const float2 Aln2, const float2 D2, float &G,
                                              float2 &dA2, float2 &dD2, float2 &db2) {
     constexpr int es = (int)sizeof(T), eo = (int)sizeof(TO);
     const int qlo = kFull ? 0 : qlo_in, qhi = kFull ? 4 : qhi_in;
@@ -105,10 +92,10 @@ __device__ __forceinline__ void cw_bwd_block(const int qlo_in, const int qhi_in,
     for (int q = 0; q < 4; ++q) {
         if (kFull || (q >= qlo && q < qhi)) {
             float2 dd[2], uu[2], Bv[2], dy[2];
-            Quad<T>::ld(td + ri.at(4 * q * es), dd);
-            Quad<T>::ld(tu + ri.at(4 * q * es), uu);
+            Quad<T>::ld(td + ri.at(wbi + 4 * q * es), dd);
+            Quad<T>::ld(tu + ri.at(wbi + 4 * q * es), uu);
             Quad<float>::ld(reinterpret_cast<const char *>(Bf + 4 * q), Bv);
-            Quad<TO>::ld(to + ro.at(4 * q * eo), dy);
+            Quad<TO>::ld(to + ro.at(wbo + 4 * q * eo), dy);
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
                 const int k = 2 * q + p;
@@ -138,10 +125,10 @@ __device__ __forceinline__ void cw_bwd_block(const int qlo_in, const int qhi_in,
     for (int q = 3; q >= 0; --q) {
         if (kFull || (q >= qlo && q < qhi)) {
             float2 dy[2], Cv[2], Bv[2], uu[2], du[2], dd[2];
-            Quad<TO>::ld(to + ro.at(4 * q * eo), dy);
+            Quad<TO>::ld(to + ro.at(wbo + 4 * q * eo), dy);
             Quad<float>::ld(reinterpret_cast<const char *>(Cf + 4 * q), Cv);
             Quad<float>::ld(reinterpret_cast<const char *>(Bf + 4 * q), Bv);
-            Quad<T>::ld(tu + ri.at(4 * q * es), uu);                    // u is still in the stage (du is written below)
+            Quad<T>::ld(tu + ri.at(wbi + 4 * q * es), uu);                    // u is still in the stage (du is written below)
 #pragma unroll
             for (int p = 1; p >= 0; --p) {
                 const int k = 2 * q + p;
@@ -161,8 +148,8 @@ __device__ __forceinline__ void cw_bwd_block(const int qlo_in, const int qhi_in,
                 dA2 = fma2(gg, mul2(R.m[k], R.hp[k]), dA2);
                 dD2 = fma2(dy[p], uu[p], dD2);
             }
-            Quad<T>::st(tu + ri.at(4 * q * es), du);                    // du replaces u, ddelta replaces delta
-            Quad<T>::st(td + ri.at(4 * q * es), dd);
+            Quad<T>::st(tu + ri.at(wbi + 4 * q * es), du);                    // du replaces u, ddelta replaces delta
+            Quad<T>::st(td + ri.at(wbi + 4 * q * es), dd);
         }
     }
     const float dBt = reduce16(v, lane, red);
@@ -173,18 +160,19 @@ template <typename T, bool kSoftplus, bool kOutF32, int kG>
 __global__ void __launch_bounds__(32, 12) ss_bwd_cw_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_d,
                                                            const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_du,
                                                            const __grid_constant__ CUtensorMap tm_dd, const __grid_constant__ CwBwdArgs a) {
-    extern __shared__ char smem_raw[];
-    // 1024-byte alignment by pointer arithmetic on the __shared__ array (a cast through an integer would make every tile
-    // access a generic LD / ST instead of LDS / STS)
-    char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    // The swizzled tiles need 1024-byte alignment.  The dynamic shared memory of a kernel without static shared memory starts at
+    // the CTA's shared window, which is allocated in 1 KB units: asserted once instead of re-aligned at run time (the re-alignment
+    // cost a register and ~10 instructions per step).
+    extern __shared__ __align__(1024) char smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     constexpr int es = (int)sizeof(T);
     constexpr int eo = kOutF32 ? 4 : es;
     using TO = typename std::conditional<kOutF32, float, T>::type;
     using raw = typename Cvt<T>::raw;
-    constexpr int RBi = kCwGrp * es, RBo = kCwGrp * eo;                  // tile row bytes: 32 or 64
+    constexpr int RBi = kCwWin * es, RBo = kCwWin * eo;                  // tile row bytes: 64 or 128
     constexpr int kTileI = 32 * RBi, kTileO = 32 * RBo;
     const int lane = threadIdx.x;
-    float *Bw = reinterpret_cast<float *>(smem + a.off_bc32), *Cw = Bw + kCwGrp;
+    float *Bw = reinterpret_cast<float *>(smem + a.off_bc32), *Cw = Bw + kCwWin;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + a.off_bar);
     const int ns = a.ns;
     if (lane == 0) {
@@ -192,13 +180,13 @@ __global__ void __launch_bounds__(32, 12) ss_bwd_cw_kernel(const __grid_constant
         fence_mbar_init();
     }
     __syncwarp();
-    const int L = a.L, ncols = kG * L, ngrp = a.ngrp;
+    const int L = a.L, ncols = kG * L, ngrp = a.ngrp, nwin = a.nwin;
     const int rows_per_item = 32 * kG;
     const int items_per_group = a.rows_per_group / rows_per_item;
     const float *Ap = reinterpret_cast<const float *>(a.A);
     const float *Dp = reinterpret_cast<const float *>(a.D);
     const float *biasp = reinterpret_cast<const float *>(a.delta_bias);
-    const SwzRow ri = swz_row_any<RBi>(lane), ro = swz_row_any<RBo>(lane);
+    const SwzRow ri = swz_row<RBi>(lane), ro = swz_row<RBo>(lane);
 
     auto item_rows = [&](int item, int &b, int &gq, int &row0) {
         const int bt = item % items_per_group;
@@ -207,18 +195,18 @@ __global__ void __launch_bounds__(32, 12) ss_bwd_cw_kernel(const __grid_constant
         row0 = gq * a.rows_per_group + bt * rows_per_item;
     };
 
-    // ---- load stream: (item, group) pairs in the order this CTA computes them (groups from the last one down), ns - 1 ahead
-    int ld_item = blockIdx.x, ld_j = ngrp - 1, ld_srow0 = 0, ld_stage = 0;
+    // ---- load stream: (item, window) pairs in the order this CTA computes them (windows from the last one down), ns - 1 ahead
+    int ld_item = blockIdx.x, ld_w = nwin - 1, ld_srow0 = 0, ld_stage = 0;
     if (ld_item < a.n_items) { int b, gq, r0; item_rows(ld_item, b, gq, r0); ld_srow0 = (b * a.dim + r0) / kG; }
     auto issue_load = [&]() {                                           // lane 0 only; no-op past the last item
         if (ld_item < a.n_items) {
             char *st = smem + ld_stage * a.stage_bytes;
             mbar_arrive_expect_tx(full + ld_stage, 2u * kTileI + kTileO);
-            tma_box_g2s(st, &tm_u, ld_j * kCwGrp, ld_srow0, full + ld_stage);
-            tma_box_g2s(st + kTileI, &tm_d, ld_j * kCwGrp, ld_srow0, full + ld_stage);
-            tma_box_g2s(st + 2 * kTileI, &tm_o, ld_j * kCwGrp, ld_srow0, full + ld_stage);
-            if (--ld_j < 0) {
-                ld_j = ngrp - 1;
+            tma_box_g2s(st, &tm_u, ld_w * kCwWin, ld_srow0, full + ld_stage);
+            tma_box_g2s(st + kTileI, &tm_d, ld_w * kCwWin, ld_srow0, full + ld_stage);
+            tma_box_g2s(st + 2 * kTileI, &tm_o, ld_w * kCwWin, ld_srow0, full + ld_stage);
+            if (--ld_w < 0) {
+                ld_w = nwin - 1;
                 ld_item += gridDim.x;
                 if (ld_item < a.n_items) { int b, gq, r0; item_rows(ld_item, b, gq, r0); ld_srow0 = (b * a.dim + r0) / kG; }
             }
@@ -230,49 +218,52 @@ __global__ void __launch_bounds__(32, 12) ss_bwd_cw_kernel(const __grid_constant
 
     uint32_t phbits = 0;
     int stage = 0;
-    // B / C elements and block states of the group about to be computed: prefetched one step ahead by 4-byte cp.async into a
-    // two-slot ring in shared memory (NOT into registers: a register live across a block gets spilled, and the spill store waits
-    // for the load -- measured: the dominant stall of the first version).  Slot: [raw B 64 B][raw C 64 B][32 block states].
-    constexpr int kEpw = 4 / es, kNw = kCwGrp / kEpw;                    // elements per 4-byte word, words per 16 columns
+    // B / C elements and the two block states of the window about to be computed: prefetched one step ahead by 4-byte cp.async
+    // into a two-slot ring in shared memory (NOT into registers: a register live across a block gets spilled, and the spill
+    // store waits for the load -- measured: the dominant stall of the first version).
+    // Slot: [raw B 128 B][raw C 128 B][block states of the lower group 128 B][of the upper group 128 B].
+    constexpr int kEpw = 4 / es, kNw = kCwWin / kEpw;                    // elements per 4-byte word; words per 32 columns (16 or 32)
     char *pf = smem + a.off_pf;
     float *red = reinterpret_cast<float *>(smem + a.off_red);
-    const raw *gBC = nullptr;                                            // this lane's B or C row of the item the prefetch is in
+    const raw *gB = nullptr, *gC = nullptr;                              // B / C rows of the item the prefetch is in
     const float *gh = nullptr;
     auto bc_rows = [&](int item) {
         if (item < a.n_items) {
             int b, gq, r0;
             item_rows(item, b, gq, r0);
-            gBC = lane < kNw ? reinterpret_cast<const raw *>(a.B) + (size_t)b * a.B_bs + (size_t)gq * a.B_gs
-                             : reinterpret_cast<const raw *>(a.C) + (size_t)b * a.C_bs + (size_t)gq * a.C_gs;
+            gB = reinterpret_cast<const raw *>(a.B) + (size_t)b * a.B_bs + (size_t)gq * a.B_gs;
+            gC = reinterpret_cast<const raw *>(a.C) + (size_t)b * a.C_bs + (size_t)gq * a.C_gs;
             gh = a.hblk + (size_t)item * ngrp * 32 + lane;
         } else {
-            gBC = nullptr;
+            gB = nullptr;
         }
     };
+    auto cp4 = [&](char *dst, const void *src, bool ok) {                // 4 bytes, zero-filled when !ok
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(ok ? src : (const void *)a.hblk), "r"(ok ? 4u : 0u)
+                     : "memory");
+    };
     int pslot = 0;
-    auto prefetch = [&](int j) {                                         // into slot `pslot`
-        char *sl = pf + pslot * 256;
-        if (lane < 2 * kNw) {
-            const int wd = lane < kNw ? lane : lane - kNw;
-            const int c = j * kCwGrp + wd * kEpw;
-            const int tk = (kG == 2 && c >= L) ? c - L : c;              // token of column c (pairs never straddle L: both even)
-            const bool ok = gBC != nullptr && c < ncols;
-            const uint32_t n = ok ? 4u : 0u;                             // src-size 0: zero fill
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(sl + (lane < kNw ? 0 : 64) + wd * 4)),
-                         "l"(ok ? (const void *)(gBC + tk) : (const void *)a.hblk), "r"(n)
-                         : "memory");
+    auto prefetch = [&](int w) {                                         // into slot `pslot`
+        char *sl = pf + pslot * 512;
+        const bool live = gB != nullptr;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {                           // part 0: B, part 1: C
+            // 2-byte types: 16 words per tensor -> lanes 0-15 copy B, lanes 16-31 copy C (one pass); fp32: 32 words each
+            const int wd = kNw == 16 ? (lane & 15) : lane;
+            const bool mine = kNw == 32 || (lane >> 4) == part;
+            if (mine) {
+                const int c = w * kCwWin + wd * kEpw;
+                const int tk = (kG == 2 && c >= L) ? c - L : c;          // token of column c (pairs never straddle L: both even)
+                cp4(sl + part * 128 + wd * 4, (part == 0 ? gB : gC) + tk, live && c < ncols);
+            }
         }
-        {
-            const bool ok = gBC != nullptr && j > 0;
-            const uint32_t n = ok ? 4u : 0u;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(sl + 128 + lane * 4)),
-                         "l"(ok ? (const void *)(gh + j * 32) : (const void *)a.hblk), "r"(n)
-                         : "memory");
-        }
+        const int j0 = 2 * w;
+        cp4(sl + 256 + lane * 4, gh + j0 * 32, live && j0 > 0);
+        cp4(sl + 384 + lane * 4, gh + (j0 + 1) * 32, live && j0 + 1 < ngrp);
         cp_async_commit();
     };
     bc_rows(blockIdx.x);
-    prefetch(ngrp - 1);
+    prefetch(nwin - 1);
 
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
         int b, gq, row0;
@@ -292,68 +283,76 @@ __global__ void __launch_bounds__(32, 12) ss_bwd_cw_kernel(const __grid_constant
             a.part_dbias[(size_t)b * a.dim + d] = db2.x + db2.y;
         };
 
-        for (int j = ngrp - 1; j >= 0; --j) {
-            const int cb = j * kCwGrp;
-            // B' = B ln2 (lanes 0-15 -> Bw), C (lanes 16-31 -> Cw) of this group's 16 columns, zero past the end; block state
+        for (int w = nwin - 1; w >= 0; --w) {
+            const int c0 = w * kCwWin;
+            // B' = B ln2 and C of this window's 32 columns as fp32 (zero past the end); the two block states
             cp_async_wait<0>();
             __syncwarp();
-            float hslot;
+            float hs0, hs1;
             {
-                const char *sl = pf + pslot * 256;
-                const raw rv = *reinterpret_cast<const raw *>(sl + (lane < 16 ? 0 : 64) + (lane & 15) * es);
-                const float f = Cvt<T>::to_f(rv);
-                Bw[lane] = lane < 16 ? f * kLn2 : f;                     // Cw == Bw + 16
-                hslot = *reinterpret_cast<const float *>(sl + 128 + lane * 4);
+                const char *sl = pf + pslot * 512;
+                Bw[lane] = Cvt<T>::to_f(*reinterpret_cast<const raw *>(sl + lane * es)) * kLn2;
+                Cw[lane] = Cvt<T>::to_f(*reinterpret_cast<const raw *>(sl + 128 + lane * es));
+                hs0 = *reinterpret_cast<const float *>(sl + 256 + lane * 4);
+                hs1 = *reinterpret_cast<const float *>(sl + 384 + lane * 4);
             }
             pslot ^= 1;
-            if (j > 0) {
-                prefetch(j - 1);
+            if (w > 0) {
+                prefetch(w - 1);
             } else {
                 bc_rows(item + gridDim.x);
-                prefetch(ngrp - 1);
+                prefetch(nwin - 1);
             }
             __syncwarp();
             mbar_wait(full + stage, (phbits >> stage) & 1u);
             phbits ^= 1u << stage;
             char *tu = smem + stage * a.stage_bytes, *td = tu + kTileI;
             const char *to = tu + 2 * kTileI;
-            const int qend = min(4, (ncols - cb) / 4);                   // quads of this group inside the tensor-map row
-            const bool split = kG == 2 && cb < L && cb + kCwGrp > L;     // the group holds the end of the even row and the start of the odd one
-            if (!split && qend == 4) {
-                const int tok0 = cb - seg * L;
-                cw_bwd_block<T, TO, kSoftplus, true>(0, 4, tok0, lane, tok0 == 0 ? 0.f : hslot, tu, td, to, ri, ro, Bw, Cw, red, accB, accC, bl2, A2, Aln2,
-                                                     D2, G, dA2, dD2, db2);
-            } else {
-                // partial group (end of the tensor-map row), or the split group: quads [qe, qend) are the head of the odd row
-                // (processed first), [0, qe) the tail of the even row
-                const int qe = split ? (L - cb) / 4 : 0;
-                for (int part = split ? 0 : 1; part < 2; ++part) {
-                    int qlo, qhi, tok0;
-                    float h0;
-                    if (split && part == 0) {
-                        qlo = qe; qhi = qend; tok0 = cb - L; h0 = 0.f;
-                    } else if (split) {
-                        flush_row();
-                        seg = 0; d -= 1;                                 // even row: fresh suffix state, its own A / D / bias
-                        Araw = __ldg(Ap + d);
-                        bl2 = splat2((biasp ? __ldg(biasp + d) : 0.f) * kLog2e); A2 = splat2(Araw); Aln2 = splat2(Araw * kLn2);
-                        D2 = splat2(Dp ? __ldg(Dp + d) : 0.f);
-                        dA2 = make_float2(0.f, 0.f); dD2 = dA2; db2 = dA2; G = 0.f;
-                        accB -= L; accC -= L;
-                        qlo = 0; qhi = qe; tok0 = cb; h0 = cb == 0 ? 0.f : hslot;
-                    } else {
-                        qlo = 0; qhi = qend; tok0 = cb - seg * L; h0 = tok0 == 0 ? 0.f : hslot;
+#pragma unroll 1
+            for (int half = 1; half >= 0; --half) {                      // the window's two 16-column groups, upper first
+                const int cb = c0 + half * kCwGrp;
+                if (cb >= ncols) continue;
+                const float hslot = half ? hs1 : hs0;
+                const int wbi = half * kCwGrp * es, wbo = half * kCwGrp * eo;
+                const float *Bf = Bw + half * kCwGrp, *Cf = Cw + half * kCwGrp;
+                const int qend = min(4, (ncols - cb) / 4);               // quads of this group inside the tensor-map row
+                const bool split = kG == 2 && cb < L && cb + kCwGrp > L; // the group holds the end of the even row and the start of the odd one
+                if (!split && qend == 4) {
+                    const int tok0 = cb - seg * L;
+                    cw_bwd_block<T, TO, kSoftplus, true>(0, 4, tok0, lane, tok0 == 0 ? 0.f : hslot, tu, td, to, ri, ro, wbi, wbo, Bf, Cf, red, accB,
+                                                         accC, bl2, A2, Aln2, D2, G, dA2, dD2, db2);
+                } else {
+                    // partial group (end of the tensor-map row), or the split group: quads [qe, qend) are the head of the odd row
+                    // (processed first), [0, qe) the tail of the even row
+                    const int qe = split ? (L - cb) / 4 : 0;
+                    for (int part = split ? 0 : 1; part < 2; ++part) {
+                        int qlo, qhi, tok0;
+                        float h0;
+                        if (split && part == 0) {
+                            qlo = qe; qhi = qend; tok0 = cb - L; h0 = 0.f;
+                        } else if (split) {
+                            flush_row();
+                            seg = 0; d -= 1;                             // even row: fresh suffix state, its own A / D / bias
+                            Araw = __ldg(Ap + d);
+                            bl2 = splat2((biasp ? __ldg(biasp + d) : 0.f) * kLog2e); A2 = splat2(Araw); Aln2 = splat2(Araw * kLn2);
+                            D2 = splat2(Dp ? __ldg(Dp + d) : 0.f);
+                            dA2 = make_float2(0.f, 0.f); dD2 = dA2; db2 = dA2; G = 0.f;
+                            accB -= L; accC -= L;
+                            qlo = 0; qhi = qe; tok0 = cb; h0 = cb == 0 ? 0.f : hslot;
+                        } else {
+                            qlo = 0; qhi = qend; tok0 = cb - seg * L; h0 = tok0 == 0 ? 0.f : hslot;
+                        }
+                        cw_bwd_block<T, TO, kSoftplus, false>(qlo, qhi, tok0, lane, h0, tu, td, to, ri, ro, wbi, wbo, Bf, Cf, red, accB, accC, bl2, A2,
+                                                              Aln2, D2, G, dA2, dD2, db2);
                     }
-                    cw_bwd_block<T, TO, kSoftplus, false>(qlo, qhi, tok0, lane, h0, tu, td, to, ri, ro, Bw, Cw, red, accB, accC, bl2, A2, Aln2, D2, G, dA2,
-                                                          dD2, db2);
                 }
             }
             // ---- du / ddelta leave with two box stores; then the stage computed one step earlier is refilled
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-                tma_box_s2g(&tm_du, tu, cb, srow0);
-                tma_box_s2g(&tm_dd, td, cb, srow0);
+                tma_box_s2g(&tm_du, tu, c0, srow0);
+                tma_box_s2g(&tm_dd, td, c0, srow0);
                 bulk_commit();
                 bulk_wait_read<1>();
                 issue_load();

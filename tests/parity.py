@@ -79,7 +79,10 @@ def long_row_scale(L: int) -> float:
 
 def cmp_auto(got: torch.Tensor, ref: torch.Tensor, what: str, n_ulp: float = 1.0, f32_scale: float = 1.0):
     """fp32 tensors by ``cmp_f32`` (tolerances times ``f32_scale``, see long_row_scale), bf16 / fp16 tensors by
-    ``cmp_stored`` (``n_ulp`` units in the last place)."""
+    ``cmp_stored`` (``n_ulp`` units in the last place).  Stored tensors of long rows: the fp32 value IN FRONT of the rounding
+    carries the noise of a recurrence over up to L tokens, which shows where terms ~RMS cancel to a small element (measured,
+    gpurun r2v, L = 6400: 1 of 19.66 M ddelta elements 3 ulp = 3.3e-3 RMS off at |value| = 0.2 RMS) -> the absolute term grows
+    with the chunk count too, a fifth as fast as the fp32 criterion."""
     if got.dtype == torch.float32:
         return cmp_f32(got, ref, what, rtol=1e-5 * f32_scale, atol_rms=2e-5 * f32_scale)
-    return cmp_stored(got, ref, got.dtype, what, n_ulp=n_ulp)
+    return cmp_stored(got, ref, got.dtype, what, n_ulp=n_ulp, atol_rms=1e-3 * max(1.0, f32_scale / 5.0))

@@ -32,8 +32,8 @@ VARIANTS = {
     "no_cw": {"MIA_NO_CW_BWD": "1"},
     "no_hblk": None,          # backward without block states: resident-row / warp-scan kernels
 }
-for _ns in (3, 4, 6, 8):
-    for _cap in (6, 8, 10, 12):
+for _ns in (2, 3, 4):
+    for _cap in (8, 10, 12):
         VARIANTS[f"cw_ns{_ns}_cap{_cap}"] = {"MIA_FORCE_CW_BWD": "1", "MIA_CW_STAGES": str(_ns), "MIA_CW_MAXPERSM": str(_cap)}
 
 
