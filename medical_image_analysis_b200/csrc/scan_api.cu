@@ -366,7 +366,7 @@ bool plan_cw_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::CwFwdArgs &r
     int best_ns = 0, best_per_sm = 0;
     double best_eff = -1.0;
     for (int ns = 4; ns >= 3; --ns) {
-        const int smem = ns * r.stage_bytes + (of32 ? 2 * tile_o : 0) + 2 * mia::kCwTok * 4 + 8 * ns + 16 + 1024;
+        const int smem = ns * r.stage_bytes + (of32 ? 2 * tile_o : 0) + 2 * mia::kCwTok * 4 + 8 * ns + 16;
         int per_sm = (227 * 1024) / (smem + 1024);
         if (per_sm > 16) per_sm = 16;
         if (per_sm < 1) continue;
@@ -380,7 +380,7 @@ bool plan_cw_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::CwFwdArgs &r
     r.off_out = r.ns * r.stage_bytes;
     r.off_bc32 = r.off_out + (of32 ? 2 * tile_o : 0);
     r.off_bar = r.off_bc32 + 2 * mia::kCwTok * 4;
-    r.smem_bytes = r.off_bar + 8 * r.ns + 16 + 1024;            // + slack for the 1024-byte alignment of the tiles
+    r.smem_bytes = r.off_bar + 8 * r.ns + 16;
     r.xchunks = mia_ss_num_chunks(L); r.xchunk_tokens = mia_ss_chunk_len(L);
     r.A = p.A; r.B = p.B; r.C = p.C; r.D = p.D; r.delta_bias = p.delta_bias; r.x = p.x; r.hblk = p.hblk;
     r.B_bs = p.B_batch_stride; r.B_gs = p.B_group_stride; r.C_bs = p.C_batch_stride; r.C_gs = p.C_group_stride;

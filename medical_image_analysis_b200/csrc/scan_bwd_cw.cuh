@@ -311,7 +311,15 @@ __global__ void __launch_bounds__(32, 12) ss_bwd_cw_kernel(const __grid_constant
 #pragma unroll 1
             for (int half = 1; half >= 0; --half) {                      // the window's two 16-column groups, upper first
                 const int cb = c0 + half * kCwGrp;
-                if (cb >= ncols) continue;
+                if (cb >= ncols) continue;                               // (only the upper group of a row's last window can be empty)
+                if (ns == 2 && half == 0 && lane == 0) {
+                    // two stages: the stage computed one step ago is the one the NEXT step needs -> refill it half a step early; its
+                    // box stores were committed at the end of that step and have had the upper group's block to be read out
+                    // (measured, L = 6400, B = 16: 0.85 -> 0.80 ms; with three stages the same early wait costs 7 %: the stores
+                    // drain slowly behind the other warps' loads, so there the refill stays at the end of the step)
+                    bulk_wait_read<0>();
+                    issue_load();
+                }
                 const float hslot = half ? hs1 : hs0;
                 const int wbi = half * kCwGrp * es, wbo = half * kCwGrp * eo;
                 const float *Bf = Bw + half * kCwGrp, *Cf = Cw + half * kCwGrp;
@@ -347,15 +355,17 @@ __global__ void __launch_bounds__(32, 12) ss_bwd_cw_kernel(const __grid_constant
                     }
                 }
             }
-            // ---- du / ddelta leave with two box stores; then the stage computed one step earlier is refilled
+            // ---- du / ddelta leave with two box stores
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
                 tma_box_s2g(&tm_du, tu, c0, srow0);
                 tma_box_s2g(&tm_dd, td, c0, srow0);
                 bulk_commit();
-                bulk_wait_read<1>();
-                issue_load();
+                if (ns > 2) {                                            // refill the stage computed one step earlier
+                    bulk_wait_read<1>();
+                    issue_load();
+                }
             }
             stage = stage + 1 == ns ? 0 : stage + 1;
         }

@@ -75,10 +75,10 @@ __device__ __forceinline__ void tma_box_s2g(const CUtensorMap *tm, const void *s
 template <typename T, bool kSoftplus, bool kOutF32, int kG>
 __global__ void __launch_bounds__(32, 16) ss_fwd_cw_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_d,
                                                            const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CwFwdArgs a) {
-    extern __shared__ char smem_raw[];
-    // 1024-byte alignment by pointer arithmetic on the __shared__ array (a cast through an integer would make every tile
-    // access a generic LD / ST instead of LDS / STS)
-    char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    // The swizzled tiles need 1024-byte alignment.  The dynamic shared memory of a kernel without static shared memory starts at
+    // the CTA's shared window, which is allocated in 1 KB units: asserted once instead of re-aligned at run time.
+    extern __shared__ __align__(1024) char smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     constexpr int es = (int)sizeof(T);
     constexpr int eo = kOutF32 ? 4 : es;
     using TO = typename std::conditional<kOutF32, float, T>::type;
