@@ -67,21 +67,23 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(kernel_key, batch):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
-    capture of this same command (profiles/*_ncu_summary.json); None if no capture is committed.  A capture taken at
-    another per-GPU batch is scaled linearly (the traffic of these kernels is proportional to the batch) and says so."""
+def ncu_traffic(kind, workload, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the `kind` ("fwd" / "bwd") kernel of `workload`, from the
+    newest committed `ncu --set full` capture of this same command (profiles/*_ncu_summary.json, written by
+    tools/ncu_summary.py); None if no capture is committed.  A capture taken at another per-GPU batch is scaled linearly (the
+    traffic of these kernels is proportional to the batch) and says so."""
     import glob
+    mult = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
     for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json")), reverse=True):
         try:
             full = json.load(open(f))
-            d = full[kernel_key]
-            rd = float(d["dram__bytes_read.sum"].split()[0]); wr = float(d["dram__bytes_write.sum"].split()[0])
-            unit = d["dram__bytes_read.sum"].split()[1]
-            mult = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
-            cap_b = int(full.get("batch", batch))
+            w = full["workloads"][workload]
+            d = full["launches"][w[kind]]
+            rd, ru = d["dram__bytes_read.sum"].split()[:2]
+            wr, wu = d["dram__bytes_write.sum"].split()[:2]
+            cap_b = int(w["B"])
             src = os.path.basename(f) if cap_b == batch else f"{os.path.basename(f)} (captured at B={cap_b}, scaled by {batch}/{cap_b})"
-            return (rd + wr) * mult * batch / cap_b, src
+            return (float(rd) * mult[ru] + float(wr) * mult[wu]) * batch / cap_b, src
         except Exception:
             continue
     return None, None
@@ -593,14 +595,15 @@ def main():
     for n, w, tk, (fb_, bb_), f_ms, b_ms in zip(names, ws, tokens, bpt, fwd_ms, bwd_ms):
         fg, bg = tk * fb_ / (f_ms * 1e-3) / 1e9, tk * bb_ / (b_ms * 1e-3) / 1e9
         per.append({"workload": n, "B": w["B"], "L": w["L"], "d_state": w["N"], "patch_tokens_per_s": tk / ((f_ms + b_ms) * 1e-3),
-                    "fwd_ms": f_ms, "bwd_ms": b_ms, "fwd": {"achieved": fg, "frac": fg / peak, "algorithmic_bytes_per_launch": tk * fb_},
-                    "bwd": {"achieved": bg, "frac": bg / peak, "algorithmic_bytes_per_launch": tk * bb_},
+                    "fwd_ms": f_ms, "bwd_ms": b_ms,
+                    "fwd": {"achieved": fg, "frac": fg / peak, "algorithmic_bytes_per_launch": tk * fb_, "traffic": ncu_traffic("fwd", n, w["B"])[0]},
+                    "bwd": {"achieved": bg, "frac": bg / peak, "algorithmic_bytes_per_launch": tk * bb_, "traffic": ncu_traffic("bwd", n, w["B"])[0]},
                     "step_frac": tk * (fb_ + bb_) / ((f_ms + b_ms) * 1e-3) / 1e9 / peak})
     dom = max(range(len(ws)), key=lambda i: bwd_ms[i])          # dominant kernel = the backward call with the largest time share
     step_bytes = sum(tk * (f + b) for tk, (f, b) in zip(tokens, bpt))
     step_gbs = step_bytes / (total_ms / args.steps * 1e-3) / 1e9
     bwd_kernel = {1: "ss_bwd_cw_kernel<bf16> (column-walk, scan_bwd_cw.cuh)", 16: "ss_bwd_rowsn_kernel<bf16>"}
-    traffic, traffic_src = ncu_traffic("bwd", ws[dom]["B"]) if names[dom] == DEFAULT else (None, None)
+    traffic, traffic_src = ncu_traffic("bwd", names[dom], ws[dom]["B"])
     roofline = {"bound": "hbm",
                 "kernel": "backward C-ABI call of %s = %s + ss_finalize_kernel (timed together, CUDA events in the timed region)"
                           % (names[dom], bwd_kernel.get(ws[dom]["N"], "ss_bwd_kernel")),
