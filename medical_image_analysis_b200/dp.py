@@ -80,6 +80,24 @@ class BucketedGradExchange:
         if wait:
             self.drain()
 
+    def measure_alone(self, device, reps: int = 3):
+        """Time the bucketed all-reduce with nothing else on the GPU (max over ranks): bus GB/s = 2 (n-1)/n x bytes / time."""
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world < 2:
+            return {}
+        self.drain()
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            for h in [dist.all_reduce(b, group=self.group, async_op=True) for b in self.buckets]:
+                h.wait()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = max_over_ranks(e0.elapsed_time(e1) / reps, device)
+        return {"alone_ms": ms, "alone_bus_gbs": 2.0 * (world - 1) / world * self.bytes_per_step / (ms * 1e-3) / 1e9}
+
     def report(self):
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         return {"bytes_per_step": self.bytes_per_step, "buckets": len(self.buckets), "world": world,
