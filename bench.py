@@ -45,6 +45,10 @@ WORKLOADS = {
 DEFAULT = "ss2d_m196_n1"
 HEADLINE = ("ss2d_m196_n1", "ss2d_m6400_n1")     # the two halves of the metric; the default run times both in every step
 GRAD_BUCKET_PARAMS = 84_000_000                  # ARM-Base / VMamba-B size: the DDP exchange of a real step
+# DDP's bucket_cap_mb: its default is 25; measured here at N = 2 (gpurun r2z, 0.34 GB per 1.66 ms step, NCCL on a high-priority
+# stream): 25 MB buckets 2.32 ms / step, 100 MB 2.04 ms, one 400 MB bucket 2.06 ms -- every bucket is its own NCCL kernel that
+# has to win whole SMs from the scan's one-warp CTAs (which fill the register files), so fewer, larger buckets overlap better
+GRAD_BUCKET_MB = 100
 METRIC = "patch-tokens/sec SS2D fwd+bwd at L=196/6400 D=768; % HBM roofline"
 
 
@@ -521,7 +525,7 @@ def main():
               else f"selective scan fwd+bwd: {desc}, R={ws[0]['R']}, G={ws[0]['G']}",
               "patch_tokens_per_step_per_gpu": sum(tokens), "bytes_per_token": [f + b for f, b in bpt],
               "l2": "working set > L2 (no flush needed)", "parallelism": f"dp{world}",
-              "grad_exchange": f"{GRAD_BUCKET_PARAMS / 1e6:.0f} M fp32 parameter gradients per step in 25 MB buckets (N > 1)",
+              "grad_exchange": f"{GRAD_BUCKET_PARAMS / 1e6:.0f} M fp32 parameter gradients per step in {GRAD_BUCKET_MB} MB buckets (N > 1)",
               "compute": "fp32 scan arithmetic on bf16 activations (dtype key = arithmetic type)"}
 
     if args.impl == "reference":
@@ -556,11 +560,25 @@ def main():
         # NCCL's kernels on a HIGH-priority stream: the scan kernels fill every SM with queued one-warp CTAs, so a collective
         # launched next to them only advances when its CTAs win the block scheduler (without it the 0.34 GB exchange did not
         # overlap at all: gpurun r2z, N = 2, 2.43 ms / step against 1.66 ms at N = 1)
+        # (stdout is parked on stderr while NCCL comes up: it prints its version banner there, and this script's stdout is ONE
+        # JSON line)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         try:
-            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
-            dist.init_process_group("nccl", device_id=dev, pg_options=opts)
-        except Exception:                                            # older constructor signatures
-            dist.init_process_group("nccl", device_id=dev)
+            try:
+                opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+                if os.environ.get("MIA_BENCH_NCCL_MAX_CTAS"):
+                    opts.config.max_ctas = int(os.environ["MIA_BENCH_NCCL_MAX_CTAS"])
+                dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+            except Exception:                                        # older constructor signatures
+                dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     from medical_image_analysis_b200 import _lib, dp
 
     inps = [make_inputs(w, dev, seed=rank + 17 * i) for i, w in enumerate(ws)]
@@ -570,7 +588,7 @@ def main():
         # DDP's gradient step for the model the scan sits in: ARM-Base-sized fp32 gradients (the scan's own dA / dD / dbias are
         # its first elements) in 25 MB buckets, all-reduced asynchronously so that they overlap the next step (as DDP
         # overlaps its buckets with the rest of the backward); the last step's exchange completes inside the timed region
-        exchange = dp.BucketedGradExchange(GRAD_BUCKET_PARAMS, dev, bucket_bytes=25 << 20)
+        exchange = dp.BucketedGradExchange(GRAD_BUCKET_PARAMS, dev, bucket_bytes=int(os.environ.get("MIA_BENCH_BUCKET_MB", str(GRAD_BUCKET_MB))) << 20)
 
         def dist_grads(g, last=False):
             exchange.step([g[2], g[5], g[6]], wait=last)

@@ -148,6 +148,8 @@ def test_scan_parity_row_serial_dstate(shape, dtype, out_float):
 def test_scan_parity_row_serial_flags(has_D, has_bias, softplus):
     _run_case(2, 64, 196, 1, 2, 64, has_D, False, has_bias, softplus, torch.bfloat16, False, seed=6)
     _run_case(1, 32, 52, 1, 1, 32, has_D, False, has_bias, softplus, torch.float32, False, seed=7)
+    # column-walk pair with two rows per tensor-map row (rows_per_group % 64 == 0), bf16 in / fp32 out
+    _run_case(2, 128, 196, 1, 2, 128, has_D, False, has_bias, softplus, torch.bfloat16, True, seed=13)
 
 
 @pytest.mark.parametrize("has_D,has_z,has_bias,softplus", list(itertools.product([False, True], repeat=4)))
