@@ -61,6 +61,26 @@ def test_chunk_geometry():
         assert lib.mia_ss_chunk_len(L) == ch and lib.mia_ss_num_chunks(L) == n, L
 
 
+def test_block_state_sizing_without_gpu():
+    """ABI 2: mia_ss_block_state_floats is a pure function of the sizes (4 bytes per 16 row-tokens, d_state 1 with 32-row
+    groups only); mia_ss_fwd_writes_block_states needs the device (and the buffers) and answers 0 without them."""
+    from medical_image_analysis_b200._lib import MiaSSParams
+    lib = _lib()
+    p = MiaSSParams()
+    p.batch, p.dim, p.seqlen, p.dstate, p.n_groups, p.delta_dim = 3, 128, 196, 1, 2, 128
+    p.itype = p.otype = 2
+    p.n_chunks = 1
+    assert lib.mia_ss_block_state_floats(ctypes.byref(p)) == 3 * 128 * 13          # ceil(196 / 16) groups per row
+    p.seqlen = 6400
+    assert lib.mia_ss_block_state_floats(ctypes.byref(p)) == 3 * 128 * 400
+    p.dstate = 16
+    assert lib.mia_ss_block_state_floats(ctypes.byref(p)) == 0                      # the d_state 16 kernels do not use them
+    p.dstate, p.dim, p.delta_dim, p.n_groups = 1, 96, 96, 2                         # 48 rows per group: not a multiple of 32
+    assert lib.mia_ss_block_state_floats(ctypes.byref(p)) == 0
+    assert lib.mia_ss_fwd_writes_block_states(ctypes.byref(p)) == 0
+    assert lib.mia_ss_fwd_writes_block_states(None) == 0
+
+
 def test_c_abi_validation_without_gpu():
     """Shape / dtype checks run before any CUDA call, so they are observable on a CPU box."""
     from medical_image_analysis_b200._lib import MiaSSParams
