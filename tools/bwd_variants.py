@@ -96,7 +96,7 @@ def main():
         out, x, _, hblk = scan_fwd(u, delta, A, Bm, Cm, Dv, None, bias, True, of32, want_block_states=True)
         base = None
         for name, env in VARIANTS.items():
-            for k in ("MIA_FORCE_WIN_BWD", "MIA_NO_WTMA_BWD", "MIA_NO_WIN_BWD", "MIA_FORCE_CW_BWD", "MIA_NO_CW_BWD", "MIA_CW_STAGES", "MIA_CW_MAXPERSM"):
+            for k in ("MIA_FORCE_CW_BWD", "MIA_NO_CW_BWD", "MIA_CW_STAGES", "MIA_CW_MAXPERSM"):
                 os.environ.pop(k, None)
             if env:
                 os.environ.update(env)
