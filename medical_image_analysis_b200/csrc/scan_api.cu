@@ -289,16 +289,24 @@ int plan_and_layout(const mia_ss_params &p, const DeviceInfo &di, bool bwd, Plan
 }
 
 // Geometry of the column-walk kernels (scan_fwd_cw.cuh / scan_bwd_cw.cuh): g rows per tensor-map row.  A pure function of the
-// problem's sizes and dtypes -- it also fixes the LAYOUT of the block states (hblk), which forward and backward must agree on:
-// for g == 2 only the column-walk kernels may write / read them.
+// problem's sizes and dtypes -- it also fixes the LAYOUT of the block states (hblk), which forward and backward must agree on.
+// A tensor-map row must be a multiple of 16 bytes (else the map cannot be encoded); it SHOULD be a multiple of 32 (else every
+// other row starts mid-sector and every 64-byte box row touches three sectors instead of two: +19 % DRAM reads measured at
+// L = 196 bf16 with g = 2).  2-byte types: the smallest g in {1, 2, 4} with g L a multiple of 16 elements, falling back to a
+// smaller legal g when rows_per_group is not a multiple of 32 g; g > 1 only for rows of one checkpoint chunk (L <= 256: the
+// kernels write x at row ends only when they walk several rows per lane).  fp32 rows (L % 4 == 0) are always legal: g = 1.
 bool cw_geometry(const mia_ss_params &p, int &g) {
     const int es = esize(p.itype), L = p.seqlen;
     if (p.dstate != 1 || p.z || p.delta_dim != p.dim || (L % 4) || p.n_groups < 1) return false;
     const int rpg = p.dim / p.n_groups;
-    if (((long long)L * es) % 16 == 0) g = 1;
-    else if (es == 2) g = 2;                                     // L % 8 == 4: two rows make a 16-byte multiple
-    else return false;
-    return rpg % (32 * g) == 0;
+    if (es == 4) { g = 1; return rpg % 32 == 0; }
+    const int want = (L % 16 == 0) ? 1 : (L % 8 == 0) ? 2 : 4;
+    for (g = want; g >= 1; g >>= 1) {
+        if (((long long)g * L * es) % 16) break;                 // not a legal tensor-map row any more
+        if (g > 1 && L > 256) continue;
+        if (rpg % (32 * g) == 0) return true;
+    }
+    return false;
 }
 
 // Row-serial forward (scan_fwd_rows.cuh): eligibility + argument block.  Returns false when the warp-scan kernels must run.
@@ -576,9 +584,9 @@ bool plan_cw_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::CwBwdArgs &r
     r.nwin = (g * L + mia::kCwWin - 1) / mia::kCwWin;
     const int tile_i = 32 * mia::kCwWin * es, tile_o = 32 * mia::kCwWin * eo;
     r.stage_bytes = 2 * tile_i + tile_o;
-    // Many short items want 8 resident warps per SM (see below) and can afford 3 stages; otherwise 2 stages (one 32-column window
-    // of lead = the 2-group lead of the 16-column ring measured best on long rows) so that 12 warps per SM fit
-    const bool many_short = r.n_items >= 4LL * 8 * di.sms;
+    // Many short rows (at least two rounds of items at 8 per SM) want 8 resident warps per SM (see below) and can afford 3
+    // stages; otherwise 2 stages with the half-step-early refill, so that 12 warps per SM fit
+    const bool many_short = L <= 256 && r.n_items >= 2LL * 8 * di.sms;
     r.ns = dbg_int("MIA_CW_STAGES", many_short ? 3 : 2);
     r.off_bc32 = r.ns * r.stage_bytes;
     r.off_pf = r.off_bc32 + 2 * mia::kCwWin * 4;                // two 512-byte prefetch slots (raw B, raw C, block states of 2 groups)
@@ -598,8 +606,8 @@ bool plan_cw_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::CwBwdArgs &r
     if (per_sm > 12) per_sm = 12;                               // 32 threads x 168 registers: 3 warps per scheduler
     // Many short items: 8 resident warps per SM finish an item 1.8x faster than 12 do (measured, gpurun r2s / r2t, bf16,
     // B = 148: L = 196 0.313 against 0.354 ms, L = 200 0.302 / 0.362, L = 100 0.173 / 0.193, L = 104 0.173 / 0.184), so with
-    // at least four rounds of items the extra rounds cost less than the contention.  Few long items (L = 1024, B = 32:
-    // 0.341 against 0.291 ms; L = 6400) want every slot.
+    // at least two rounds of short rows the extra rounds cost less than the contention.  Long rows (L = 1024, B = 32: 0.341
+    // against 0.291 ms; L = 6400) want every slot.
     if (many_short && per_sm > 8) per_sm = 8;
     per_sm = std::min(per_sm, dbg_int("MIA_CW_MAXPERSM", per_sm));
     if (per_sm < 1) return false;

@@ -12,8 +12,8 @@
 //     re-derived in the suffix loop from them and from u / B, which are still in the stage; dC is reduced over the rows right
 //     after the recompute and dB after the suffix loop (two 16-value butterflies, 32 shuffles, instead of one of 32 values);
 //   * 128 registers, ~13 KB of shared memory per warp: 15-16 resident one-warp CTAs per SM, no barrier.
-// Rows of 392 bytes (L = 196 bf16) are walked two to a tensor-map row (g = 2) exactly like the forward: the odd row first
-// (columns [L, 2 L) from the end), then the even row; the group that holds column L is split between them.
+// Rows of 392 bytes (L = 196 bf16) are walked g = 4 (or 2) to a tensor-map row exactly like the forward, last row first (columns
+// [(g - 1) L, g L) from the end), ...; a group that holds a multiple of L is split between the two rows it touches.
 // Reductions over rows (dB, dC): the same transposing butterfly as scan_bwd_rows.cuh, one partial per (32 rows, token) in the
 // workspace, folded in a fixed order by the finalize kernel -> deterministic.
 // Preconditions (host-checked): as scan_fwd_cw.cuh, block states present, dense 16-byte aligned u / delta / dout / du / ddelta.
@@ -253,7 +253,9 @@ __global__ void __launch_bounds__(32, 12) ss_bwd_cw_kernel(const __grid_constant
             const bool mine = kNw == 32 || (lane >> 4) == part;
             if (mine) {
                 const int c = w * kCwWin + wd * kEpw;
-                const int tk = (kG == 2 && c >= L) ? c - L : c;          // token of column c (pairs never straddle L: both even)
+                int tk = c;                                              // token of column c: c mod L (pairs never straddle a row end: L is even)
+#pragma unroll
+                for (int i = 1; i < kG; ++i) tk -= tk >= L ? L : 0;
                 cp4(sl + part * 128 + wd * 4, (part == 0 ? gB : gC) + tk, live && c < ncols);
             }
         }
@@ -323,35 +325,34 @@ __global__ void __launch_bounds__(32, 12) ss_bwd_cw_kernel(const __grid_constant
                 const float hslot = half ? hs1 : hs0;
                 const int wbi = half * kCwGrp * es, wbo = half * kCwGrp * eo;
                 const float *Bf = Bw + half * kCwGrp, *Cf = Cw + half * kCwGrp;
-                const int qend = min(4, (ncols - cb) / 4);               // quads of this group inside the tensor-map row
-                const bool split = kG == 2 && cb < L && cb + kCwGrp > L; // the group holds the end of the even row and the start of the odd one
-                if (!split && qend == 4) {
+                const int hi0 = min(cb + kCwGrp, ncols);                  // columns [cb, hi0) of this group lie inside the tensor-map row
+                if (hi0 == cb + kCwGrp && (kG == 1 || cb >= seg * L)) {  // a whole group inside the current row
                     const int tok0 = cb - seg * L;
                     cw_bwd_block<T, TO, kSoftplus, true>(0, 4, tok0, lane, tok0 == 0 ? 0.f : hslot, tu, td, to, ri, ro, wbi, wbo, Bf, Cf, red, accB,
                                                          accC, bl2, A2, Aln2, D2, G, dA2, dD2, db2);
                 } else {
-                    // partial group (end of the tensor-map row), or the split group: quads [qe, qend) are the head of the odd row
-                    // (processed first), [0, qe) the tail of the even row
-                    const int qe = split ? (L - cb) / 4 : 0;
-                    for (int part = split ? 0 : 1; part < 2; ++part) {
-                        int qlo, qhi, tok0;
-                        float h0;
-                        if (split && part == 0) {
-                            qlo = qe; qhi = qend; tok0 = cb - L; h0 = 0.f;
-                        } else if (split) {
+                    // partial group (end of the tensor-map row) and / or a group that holds the end of one row and the start of
+                    // the next (of several, for rows shorter than a group): sub-blocks from the high columns down, one per row
+                    int hi = hi0;
+                    while (hi > cb) {
+                        const int row_lo = seg * L;                      // first column of the current row
+                        if (kG > 1 && hi <= row_lo) {                    // the current row is finished: switch to the one before it
                             flush_row();
-                            seg = 0; d -= 1;                             // even row: fresh suffix state, its own A / D / bias
+                            seg -= 1; d -= 1;                            // fresh suffix state, its own A / D / bias
                             Araw = __ldg(Ap + d);
                             bl2 = splat2((biasp ? __ldg(biasp + d) : 0.f) * kLog2e); A2 = splat2(Araw); Aln2 = splat2(Araw * kLn2);
                             D2 = splat2(Dp ? __ldg(Dp + d) : 0.f);
                             dA2 = make_float2(0.f, 0.f); dD2 = dA2; db2 = dA2; G = 0.f;
                             accB -= L; accC -= L;
-                            qlo = 0; qhi = qe; tok0 = cb; h0 = cb == 0 ? 0.f : hslot;
-                        } else {
-                            qlo = 0; qhi = qend; tok0 = cb - seg * L; h0 = tok0 == 0 ? 0.f : hslot;
+                            continue;
                         }
-                        cw_bwd_block<T, TO, kSoftplus, false>(qlo, qhi, tok0, lane, h0, tu, td, to, ri, ro, wbi, wbo, Bf, Cf, red, accB, accC, bl2, A2,
-                                                              Aln2, D2, G, dA2, dD2, db2);
+                        const int lo = kG > 1 ? max(cb, row_lo) : cb;
+                        // the block state of the group is the state entering column cb: valid for the sub-block that starts there,
+                        // unless that column is the first token of the row
+                        const float h0 = lo == row_lo ? 0.f : hslot;
+                        cw_bwd_block<T, TO, kSoftplus, false>((lo - cb) / 4, (hi - cb) / 4, cb - row_lo, lane, h0, tu, td, to, ri, ro, wbi, wbo, Bf, Cf,
+                                                              red, accB, accC, bl2, A2, Aln2, D2, G, dA2, dD2, db2);
+                        hi = lo;
                     }
                 }
             }
@@ -389,6 +390,7 @@ template <typename T>
 cudaError_t launch_bwd_cw(const CUtensorMap *tm, const CwBwdArgs &a, int grid, bool dout_f32, cudaStream_t stream) {
     if constexpr (sizeof(T) == 2) {
         if (a.g == 2) return launch_bwd_cw_g<T, 2>(tm, a, grid, dout_f32, stream);
+        if (a.g == 4) return launch_bwd_cw_g<T, 4>(tm, a, grid, dout_f32, stream);
     }
     return a.g == 1 ? launch_bwd_cw_g<T, 1>(tm, a, grid, dout_f32, stream) : cudaErrorInvalidValue;
 }

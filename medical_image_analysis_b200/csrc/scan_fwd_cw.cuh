@@ -13,10 +13,13 @@
 //     resident all at once instead of 1.3 rounds;
 //   * tiles carry the TMA swizzle whose span is the tile row (64 B -> SWIZZLE_64B, 128 B -> SWIZZLE_128B): the 32 lanes read
 //     the same column of 32 different rows, which unswizzled would hit 2-4 banks.
-// Rows whose byte pitch is not a multiple of 16 (L = 196 bf16: 392 B) cannot be a tensor-map row; TWO consecutive rows can
-// (784 B).  The tensor is then mapped as [rows / 2][2 L] (g = 2) and a lane walks its even row (columns [0, L)) and then its
-// odd row (columns [L, 2 L)) as one sequence, resetting the state at column L.  Box starts stay multiples of 32 columns, i.e.
-// 16-byte aligned (a box starting at an odd row's first token would not be, and the TMA unit traps on it).
+// Rows whose byte pitch is not a multiple of 16 (L = 196 bf16: 392 B) cannot be a tensor-map row; g = 2 or 4 consecutive rows
+// can.  The tensor is then mapped as [rows / g][g L] and a lane walks its g rows one after the other (columns [s L, (s + 1) L)
+// are row s) as one sequence, resetting the state at every multiple of L.  Box starts stay multiples of 32 columns, i.e.
+// 16-byte aligned (a box starting at an odd row's first token would not be, and the TMA unit traps on it).  g is the smallest
+// of 1, 2, 4 that makes the tensor-map row a multiple of 32 BYTES (L = 196 bf16: g = 4, 1568 B): with a 784-byte pitch every
+// second tensor-map row starts in the middle of a 32-byte sector, each 64-byte box row then touches three sectors, and the
+// forward read 19 % more DRAM bytes than it needed (ncu, profiles/r2z_ncu_summary.json).
 //
 // Block states for the backward (hblk): the state entering every 16-COLUMN group, slot j = column / 16, layout
 // [item][ngrp][32 lanes].  For g = 1 that is the state entering token 16 j; for g = 2 the odd row's slots sit at tokens
@@ -148,7 +151,9 @@ __global__ void __launch_bounds__(32, 16) ss_fwd_cw_kernel(const __grid_constant
     };
     auto fetch_bc = [&](int w) {
         const int c = w * kCwTok + lane;
-        const int tk = (kG == 2 && c >= L) ? c - L : c;                  // token of column c
+        int tk = c;                                                      // token of column c: c mod L
+#pragma unroll
+        for (int i = 1; i < kG; ++i) tk -= tk >= L ? L : 0;
         const bool ok = gB != nullptr && c < ncols;
         bnext = ok ? __ldg(gB + tk) : (raw)0;
         cnext = ok ? __ldg(gC + tk) : (raw)0;
@@ -160,7 +165,8 @@ __global__ void __launch_bounds__(32, 16) ss_fwd_cw_kernel(const __grid_constant
         int b, gq, row0;
         item_rows(item, b, gq, row0);
         const int srow0 = (b * a.dim + row0) / kG;
-        int d = row0 + kG * lane;                                        // row of the current segment (even row first)
+        int seg = 0;                                                     // row of the tensor-map row being walked
+        int d = row0 + kG * lane;
         float Araw = __ldg(Ap + d);
         float2 bl2 = splat2((biasp ? __ldg(biasp + d) : 0.f) * kLog2e), A2 = splat2(Araw), D2 = splat2(Dp ? __ldg(Dp + d) : 0.f);
         float h = 0.f;
@@ -230,19 +236,26 @@ __global__ void __launch_bounds__(32, 16) ss_fwd_cw_kernel(const __grid_constant
                 if (tok_end == L || (tok_end & (a.xchunk_tokens - 1)) == 0) xrow[xc++] = make_float2(ex2f(Araw * (msum.x + msum.y)), h);
             };
             const int cend = min(c0 + kCwTok, ncols);
-            if (kG == 2 && c0 < L && cend > L) {
-                run(c0, L);                                              // tail of the even row
-                checkpoint(L);
-                d += 1;                                                  // odd row: fresh state, its own A / D / bias
-                Araw = __ldg(Ap + d);
-                bl2 = splat2((biasp ? __ldg(biasp + d) : 0.f) * kLog2e); A2 = splat2(Araw); D2 = splat2(Dp ? __ldg(Dp + d) : 0.f);
-                h = 0.f; msum = make_float2(0.f, 0.f);
-                xrow += a.xchunks; xc = 0;
-                run(L, cend);
-                checkpoint(cend - L);
-            } else {
+            if (kG == 1) {
                 run(c0, cend);
-                checkpoint((kG == 2 && c0 >= L) ? cend - L : cend);
+                checkpoint(cend);
+            } else {
+                // the window may hold the end of one row and the start of the next (several, for rows shorter than a window)
+                int c = c0;
+                while (c < cend) {
+                    const int row_end = (seg + 1) * L;
+                    const int e = min(cend, row_end);
+                    run(c, e);
+                    checkpoint(e - seg * L);
+                    if (e == row_end && seg + 1 < kG) {                  // next row: fresh state, its own A / D / bias
+                        ++seg; d += 1;
+                        Araw = __ldg(Ap + d);
+                        bl2 = splat2((biasp ? __ldg(biasp + d) : 0.f) * kLog2e); A2 = splat2(Araw); D2 = splat2(Dp ? __ldg(Dp + d) : 0.f);
+                        h = 0.f; msum = make_float2(0.f, 0.f);
+                        xrow += a.xchunks; xc = 0;
+                    }
+                    c = e;
+                }
             }
             // ---- the window's y leaves with one box store; then the stage computed one step earlier is refilled
             fence_proxy_async();                                         // generic-proxy tile writes -> TMA store
@@ -275,6 +288,7 @@ template <typename T>
 cudaError_t launch_fwd_cw(const CUtensorMap *tm, const CwFwdArgs &a, int grid, bool out_f32, cudaStream_t stream) {
     if constexpr (sizeof(T) == 2) {
         if (a.g == 2) return launch_fwd_cw_g<T, 2>(tm, a, grid, out_f32, stream);
+        if (a.g == 4) return launch_fwd_cw_g<T, 4>(tm, a, grid, out_f32, stream);
     }
     return a.g == 1 ? launch_fwd_cw_g<T, 1>(tm, a, grid, out_f32, stream) : cudaErrorInvalidValue;
 }

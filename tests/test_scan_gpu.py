@@ -99,7 +99,11 @@ ROWS = [(2, 64, 196, 1, 2, 64), (1, 32, 4, 1, 1, 32), (2, 96, 16, 1, 3, 96), (1,
         (2, 32, 300, 1, 1, 32), (1, 64, 292, 1, 2, 64), (3, 32, 324, 1, 1, 32),
         # column-walk forward, two rows per tensor-map row (L * 2 bytes % 16 == 8, rows_per_group % 64 == 0)
         (2, 128, 196, 1, 2, 128), (1, 64, 4, 1, 1, 64), (2, 64, 36, 1, 1, 64), (1, 128, 100, 1, 2, 128), (1, 64, 204, 1, 1, 64),
-        (3, 64, 12, 1, 1, 64), (1, 64, 28, 1, 1, 64)]
+        (3, 64, 12, 1, 1, 64), (1, 64, 28, 1, 1, 64),
+        # ... two rows per tensor-map row because that makes it a multiple of 32 bytes (L % 16 == 8), four rows (L % 8 == 4,
+        # rows_per_group % 128 == 0), four rows shorter than one 16-column group
+        (2, 64, 200, 1, 1, 64), (1, 64, 24, 1, 1, 64), (2, 128, 104, 1, 1, 128), (2, 256, 196, 1, 2, 256), (1, 128, 4, 1, 1, 128),
+        (2, 128, 36, 1, 1, 128), (1, 128, 12, 1, 1, 128)]
 
 
 @pytest.mark.parametrize("shape", ROWS, ids=[f"b{s[0]}d{s[1]}L{s[2]}G{s[4]}" for s in ROWS])
@@ -124,8 +128,9 @@ CW_G2 = [(10, 2048, 196, 1, 2, 2048), (19, 1024, 36, 1, 1, 1024), (19, 1024, 12,
 @pytest.mark.parametrize("shape", CW_G2, ids=[f"b{s[0]}d{s[1]}L{s[2]}G{s[4]}" for s in CW_G2])
 @pytest.mark.parametrize("dtype,out_float", [(torch.bfloat16, False), (torch.bfloat16, True), (torch.float16, False)], ids=["bf16", "bf16o32", "f16"])
 def test_scan_parity_column_walk_two_rows_per_map_row(shape, dtype, out_float):
-    """Column-walk forward AND backward with two rows per tensor-map row (row pitch % 16 == 8 bytes): the backward takes that
-    path from 4 x 148 32-row items on.  Split group (the one holding column L), partial last group, L < 16."""
+    """Column-walk forward AND backward with several rows per tensor-map row (row pitch % 16 == 8 bytes; four rows here:
+    rows_per_group % 128 == 0) at sizes with many rounds of items.  Split groups (those holding a multiple of L), partial last
+    group, L < 16."""
     batch, dim, L, N, G, ddim = shape
     _run_case(batch, dim, L, N, G, ddim, True, False, True, True, dtype, out_float, seed=12, fs_mult=2.0)
 

@@ -32,8 +32,8 @@ VARIANTS = {
     "no_cw": {"MIA_NO_CW_BWD": "1"},
     "no_hblk": None,          # backward without block states: resident-row / warp-scan kernels
 }
-for _ns in (2, 3, 4):
-    for _cap in (8, 10, 12):
+for _ns in (2, 3):
+    for _cap in (8, 12):
         VARIANTS[f"cw_ns{_ns}_cap{_cap}"] = {"MIA_FORCE_CW_BWD": "1", "MIA_CW_STAGES": str(_ns), "MIA_CW_MAXPERSM": str(_cap)}
 
 
@@ -65,7 +65,7 @@ def main():
         fbase = None
         fvars = [("fwd_default", {}), ("fwd_no_cw", {"MIA_NO_CW_FWD": "1"})]
         for _ns in (3, 4):
-            for _cap in (6, 8, 10, 12, 16):
+            for _cap in (8, 12, 16):
                 fvars.append((f"fwd_cw_ns{_ns}_cap{_cap}", {"MIA_CW_STAGES": str(_ns), "MIA_CW_MAXPERSM": str(_cap)}))
         for name, env in fvars:
             for k in ("MIA_NO_CW_FWD", "MIA_CW_STAGES", "MIA_FORCE_CW_FWD", "MIA_CW_MAXPERSM"):
