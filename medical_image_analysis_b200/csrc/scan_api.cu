@@ -289,23 +289,35 @@ int plan_and_layout(const mia_ss_params &p, const DeviceInfo &di, bool bwd, Plan
 }
 
 // Geometry of the column-walk kernels (scan_fwd_cw.cuh / scan_bwd_cw.cuh): g rows per tensor-map row.  A pure function of the
-// problem's sizes and dtypes -- it also fixes the LAYOUT of the block states (hblk), which forward and backward must agree on.
+// problem's sizes and dtypes (and the SM count) -- it also fixes the LAYOUT of the block states (hblk), which forward and backward must agree on.
 // A tensor-map row must be a multiple of 16 bytes (else the map cannot be encoded); it SHOULD be a multiple of 32 (else every
 // other row starts mid-sector and every 64-byte box row touches three sectors instead of two: +19 % DRAM reads measured at
 // L = 196 bf16 with g = 2).  2-byte types: the smallest g in {1, 2, 4} with g L a multiple of 16 elements, falling back to a
-// smaller legal g when rows_per_group is not a multiple of 32 g; g > 1 only for rows of one checkpoint chunk (L <= 256: the
-// kernels write x at row ends only when they walk several rows per lane).  fp32 rows (L % 4 == 0) are always legal: g = 1.
-bool cw_geometry(const mia_ss_params &p, int &g) {
+// smaller legal g when rows_per_group is not a multiple of 32 g or when the item count falls between one and two rounds; g > 1
+// only for rows of one checkpoint chunk (L <= 256: the kernels write x at row ends only when they walk several rows per
+// lane).  fp32 rows (L % 4 == 0) are always legal: g = 1.
+bool cw_geometry(const mia_ss_params &p, int sms, int &g) {
     const int es = esize(p.itype), L = p.seqlen;
     if (p.dstate != 1 || p.z || p.delta_dim != p.dim || (L % 4) || p.n_groups < 1) return false;
     const int rpg = p.dim / p.n_groups;
     if (es == 4) { g = 1; return rpg % 32 == 0; }
     const int want = (L % 16 == 0) ? 1 : (L % 8 == 0) ? 2 : 4;
-    for (g = want; g >= 1; g >>= 1) {
-        if (((long long)g * L * es) % 16) break;                 // not a legal tensor-map row any more
-        if (g > 1 && L > 256) continue;
-        if (rpg % (32 * g) == 0) return true;
+    // Items are 32 g rows: a larger g halves their number, and a problem that fills the resident slots a little more than once
+    // pays a whole second round (measured, gpurun r2fin2, B = 64, L = 196, fp32 out: 1536 items on 1332 - 1480 slots, forward
+    // 0.079 -> 0.103 ms) -> take the preferred g when its items fit one round or make at least two, else the next smaller
+    // legal one.  (~9 resident warps per SM with fp32 outputs / gradients, 12 otherwise; the same estimate for both directions,
+    // since forward and backward must pick the same g.)
+    const long long slots = (long long)sms * ((esize(p.otype) == 4) ? 9 : 12);
+    int fallback = 0;
+    for (int c = want; c >= 1; c >>= 1) {
+        if (((long long)c * L * es) % 16) break;                 // not a legal tensor-map row any more
+        if (c > 1 && L > 256) continue;
+        if (rpg % (32 * c)) continue;
+        const long long n_items = (long long)p.batch * p.n_groups * (rpg / (32 * c));
+        if (n_items <= slots || n_items >= 2 * slots) { g = c; return true; }
+        if (!fallback) fallback = c;
     }
+    if (fallback) { g = fallback; return true; }
     return false;
 }
 
@@ -349,7 +361,7 @@ bool plan_rows_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsArgs &
 bool plan_cw_fwd(const mia_ss_params &p, const DeviceInfo &di, mia::CwFwdArgs &r, CUtensorMap *tm, int &grid) {
     const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
     int g = 0;
-    if (!cw_geometry(p, g)) return false;
+    if (!cw_geometry(p, di.sms, g)) return false;
     if (dbg_knob("MIA_NO_CW_FWD")) return false;
     const int rpg = p.dim / p.n_groups;
     auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
@@ -565,7 +577,7 @@ bool plan_rows_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::RowsBwdArg
 bool plan_cw_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::CwBwdArgs &r, CUtensorMap *tm, int &grid) {
     const int es = esize(p.itype), eo = esize(p.otype), L = p.seqlen;
     int g = 0;
-    if (!p.hblk || !cw_geometry(p, g)) return false;
+    if (!p.hblk || !cw_geometry(p, di.sms, g)) return false;
     if (dbg_knob("MIA_NO_CW_BWD")) return false;
     const int rpg = p.dim / p.n_groups;
     auto dense = [&](long long bs, long long ds) { return ds == L && bs == (long long)p.dim * L; };
