@@ -9,9 +9,13 @@ shapes (d_inner 768 -> R = 4 x 768 = 3072 scan rows, G = 4 B/C groups, d_state 1
 patch-token = one (image, position) over all R rows; `value` = patch-tokens of both halves / time of both halves (inputs
 resident in HBM).  `--workload NAME` times a single workload instead.  `e2e` goes through the same C-ABI calls but starts from
 pinned HOST buffers and ends with the results back in host memory (copies inside the timed region).
-N > 1 (torchrun): pure data parallelism, per-GPU batch fixed (weak scaling); every step ends with the DDP gradient exchange of
-the model the scan sits in (ARM-Base: 84 M parameters = 0.34 GB fp32, 25 MB buckets, NCCL all-reduce issued asynchronously
-through medical_image_analysis_b200.dp) -- the scan itself has no collective (multi-GPU).
+N > 1 (torchrun): pure data parallelism, per-GPU batch fixed (weak scaling).  The scan itself has no collective; the one
+exchange of the path is DDP's gradient all-reduce of the model the scan sits in (VMamba-B / ARM-Base: 84 M parameters = 0.34 GB
+fp32, DDP's 25 MB buckets, NCCL all-reduce issued asynchronously through medical_image_analysis_b200.dp).  A bench step is ONE
+SS2D layer's scan, and VMamba-B runs 15 layers of exactly the headline shape (stage 3: 14 x 14 tokens, d_inner 768) per training
+step, so the gradient set leaves at DDP's cadence: one bucket per step, round robin = 0.34 GB per 14 steps (`config.grad_exchange`).
+The line also carries the stress variant -- the WHOLE 0.34 GB set all-reduced after EVERY scan step, 14 x the traffic of a real
+step -- measured right after the timed region (`grad_exchange.every_step`) (multi-GPU).
 """
 import argparse
 import json
@@ -45,10 +49,15 @@ WORKLOADS = {
 DEFAULT = "ss2d_m196_n1"
 HEADLINE = ("ss2d_m196_n1", "ss2d_m6400_n1")     # the two halves of the metric; the default run times both in every step
 GRAD_BUCKET_PARAMS = 84_000_000                  # ARM-Base / VMamba-B size: the DDP exchange of a real step
-# DDP's bucket_cap_mb: its default is 25; measured here at N = 2 (gpurun r2z, 0.34 GB per 1.66 ms step, NCCL on a high-priority
-# stream): 25 MB buckets 2.32 ms / step, 100 MB 2.04 ms, one 400 MB bucket 2.06 ms -- every bucket is its own NCCL kernel that
-# has to win whole SMs from the scan's one-warp CTAs (which fill the register files), so fewer, larger buckets overlap better
-GRAD_BUCKET_MB = 100
+GRAD_BUCKET_MB = 25                              # DDP's default bucket_cap_mb -> 13 buckets
+# One bench step = the scan of ONE SS2D layer; the model that owns the 84 M parameters runs 15 layers of the headline shape per
+# training step (VMamba-B, depths [2, 2, 15, 2]: stage 3 = 14 x 14 tokens, d_model 384 -> d_inner 768;
+# R2GenCSR/VMamba/classification/configs/vssm/vmambav2_base_224.yaml), so its gradient set is exchanged once per 15 scan steps,
+# bucket by bucket as the backward walks the layers: ceil(13 / 15) = 1 bucket per step.
+# The stress variant (all 13 buckets after EVERY scan step = 0.34 GB per 1.66 ms, which no training step of this model asks for)
+# is measured too and reported next to it; at N = 2 / 4 it ran 2.04 / 2.54 ms per step with 100 MB buckets (gpurun r2z).
+MODEL_SCAN_LAYERS = 15
+GRAD_BUCKETS_PER_STEP = 1
 METRIC = "patch-tokens/sec SS2D fwd+bwd at L=196/6400 D=768; % HBM roofline"
 
 
@@ -525,7 +534,9 @@ def main():
               else f"selective scan fwd+bwd: {desc}, R={ws[0]['R']}, G={ws[0]['G']}",
               "patch_tokens_per_step_per_gpu": sum(tokens), "bytes_per_token": [f + b for f, b in bpt],
               "l2": "working set > L2 (no flush needed)", "parallelism": f"dp{world}",
-              "grad_exchange": f"{GRAD_BUCKET_PARAMS / 1e6:.0f} M fp32 parameter gradients per step in {GRAD_BUCKET_MB} MB buckets (N > 1)",
+              "grad_exchange": f"N > 1: DDP gradient set of the model ({GRAD_BUCKET_PARAMS / 1e6:.0f} M fp32 = {GRAD_BUCKET_PARAMS * 4 / 1e9:.2f} GB) in "
+                               f"{GRAD_BUCKET_MB} MB buckets, {GRAD_BUCKETS_PER_STEP} bucket per scan step round robin (a step = one of the "
+                               f"model's {MODEL_SCAN_LAYERS} SS2D layers of this shape); stress variant (whole set every step) in grad_exchange.every_step",
               "compute": "fp32 scan arithmetic on bf16 activations (dtype key = arithmetic type)"}
 
     if args.impl == "reference":
@@ -588,7 +599,8 @@ def main():
         # DDP's gradient step for the model the scan sits in: ARM-Base-sized fp32 gradients (the scan's own dA / dD / dbias are
         # its first elements) in 25 MB buckets, all-reduced asynchronously so that they overlap the next step (as DDP
         # overlaps its buckets with the rest of the backward); the last step's exchange completes inside the timed region
-        exchange = dp.BucketedGradExchange(GRAD_BUCKET_PARAMS, dev, bucket_bytes=int(os.environ.get("MIA_BENCH_BUCKET_MB", str(GRAD_BUCKET_MB))) << 20)
+        exchange = dp.BucketedGradExchange(GRAD_BUCKET_PARAMS, dev, bucket_bytes=int(os.environ.get("MIA_BENCH_BUCKET_MB", str(GRAD_BUCKET_MB))) << 20,
+                                           buckets_per_step=GRAD_BUCKETS_PER_STEP)
 
         def dist_grads(g, last=False):
             exchange.step([g[2], g[5], g[6]], wait=last)
@@ -615,8 +627,22 @@ def main():
     e2e_ms = dp.max_over_ranks(e2e_ms, dev)
     e2e_value = tokens[0] * world * e2e_steps / (e2e_ms * 1e-3)
 
-    # the exchange alone (outside the timed region, EVERY rank takes part): achieved all-reduce bus bandwidth of this box
-    exchange_alone = exchange.measure_alone(dev) if exchange is not None else {}
+    # the exchange alone (outside the timed region, EVERY rank takes part): achieved all-reduce bus bandwidth of this box; and
+    # the stress variant: the same K steps with the WHOLE gradient set all-reduced after every scan step (100 MB buckets: the
+    # better of the bucket sizes measured for it)
+    exchange_alone, stress = {}, {}
+    if exchange is not None:
+        exchange_alone = exchange.measure_alone(dev)
+        ex_all = dp.BucketedGradExchange(GRAD_BUCKET_PARAMS, dev, bucket_bytes=100 << 20)
+        exchange.drain()
+        run_device_steps(inps, 2, 0, lambda g, last=False: ex_all.step([g[2], g[5], g[6]], wait=last))
+        dist.barrier()
+        s_ms, _, _ = run_device_steps(inps, args.steps, 0, lambda g, last=False: ex_all.step([g[2], g[5], g[6]], wait=last))
+        s_ms = dp.max_over_ranks(s_ms, dev)
+        stress = {"every_step": {"value": sum(tokens) * world * args.steps / (s_ms * 1e-3), "ms_per_step": s_ms / args.steps,
+                                 "bytes_per_step": ex_all.model_bytes, "bucket_mb": 100,
+                                 "note": "whole gradient set all-reduced after EVERY scan step (not the headline: %dx a real step's traffic)"
+                                         % MODEL_SCAN_LAYERS}}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -658,6 +684,7 @@ def main():
     if exchange is not None:
         line["grad_exchange"] = exchange.report()
         line["grad_exchange"].update(exchange_alone)
+        line["grad_exchange"].update(stress)
 
     if not args.no_extras and world == 1:
         extras = []

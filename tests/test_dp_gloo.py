@@ -31,6 +31,18 @@ def _worker(rank, world, port, q):
         ex.step([torch.full((3,), 2.0 * (rank + 1)), None, torch.full((2,), 1.0)], wait=True)     # waits for the first, completes the second
         assert torch.equal(ex.flat[:5], torch.tensor([6.0, 6.0, 6.0, 2.0, 2.0])), ex.flat
         assert ex.report()["bytes_per_step"] == 52 and ex.report()["world"] == 2
+        # the layer cadence: one bucket per step, round robin (a gradient set leaves over 4 steps); only the bucket whose turn it
+        # is gets summed over the ranks
+        rr = BucketedGradExchange(13, "cpu", bucket_bytes=16, buckets_per_step=1)
+        rr.flat.fill_(float(rank + 1))
+        for k in range(3):
+            rr.step([], wait=(k == 2))
+        want = torch.tensor([3.0] * 12 + [float(rank + 1)])
+        assert torch.equal(rr.flat, want), rr.flat
+        rep = rr.report()
+        assert rep["steps_per_gradient_set"] == 4 and rep["bytes_per_step"] == 13.0 and rr.bytes_sent == 48 and rr.cursor == 3
+        rr.step([], wait=True)                                                       # the short tail bucket, then wrap around
+        assert rr.flat[12].item() == 3.0 and rr.cursor == 0
         mine = shard_batch(7, rank, world)
         counts = [torch.zeros(1) for _ in range(world)]
         dist.all_gather(counts, torch.tensor([float(len(mine))]))
