@@ -623,6 +623,9 @@ bool plan_cw_bwd(const mia_ss_params &p, const DeviceInfo &di, mia::CwBwdArgs &r
     if (many_short && per_sm > 8) per_sm = 8;
     per_sm = std::min(per_sm, dbg_int("MIA_CW_MAXPERSM", per_sm));
     if (per_sm < 1) return false;
+    // at most 8 resident warps per SM: the build that may use 255 registers (scan_bwd_cw.cuh, kMinBlk); same results
+    r.wide = dbg_int("MIA_CW_WIDE", per_sm <= 8 ? 1 : 0);
+    if (r.wide && per_sm > 8) per_sm = 8;
     const long long slots = (long long)di.sms * per_sm;
     const long long rounds = (r.n_items + slots - 1) / slots;
     grid = (int)((r.n_items + rounds - 1) / rounds);             // equal rounds per CTA

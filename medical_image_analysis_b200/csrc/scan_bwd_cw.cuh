@@ -28,6 +28,9 @@
 
 namespace mia {
 
+#ifndef MIA_CW_FMA
+#define MIA_CW_FMA 0             // 1: h_t by one FFMA (a_t h_{t-1} off the serial chain); measured slower in the 168-register build (tools/ab_cw.py)
+#endif
 constexpr int kCwGrp = 16;       // columns per group = tokens per recompute block
 constexpr int kCwWin = 32;       // columns per window = per stage of the ring (two groups)
 
@@ -35,6 +38,7 @@ struct CwBwdArgs {
     int batch, dim, L, G, rows_per_group;
     int softplus;
     int g, n_items, ngrp, nwin, ns;         // rows per tensor-map row; items of 32 g rows; 16-column groups / 32-column windows per tensor-map row; stages
+    int wide;                               // at most 8 resident warps per SM planned: the build with up to 255 registers per thread
     int stage_bytes, off_bc32, off_pf, off_red, off_bar, smem_bytes;
     const void *A, *B, *C, *D, *delta_bias;
     const float *hblk;
@@ -87,18 +91,39 @@ __device__ __forceinline__ void cw_bwd_block(const int qlo_in, const int qhi_in,
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = 0.f;
     float h = h0;
+    // Tile accesses: one quad (4 tokens) at a time, or -- whole blocks of 2-byte types -- two quads = ONE 16-byte access per tile
+    // and lane, which is conflict-free on the swizzled tile where the 8-byte accesses are not (Oct, scan_fwd_rows.cuh).
+    constexpr bool kOct = kFull && es == 2 && MIA_CW_OCT;
+    constexpr int kNQ = kOct ? 2 : 1, kNP = 2 * kNQ, kNS = 4 / kNQ;
+    auto ld_in = [&](const char *tile, const int q0, float2(&f)[kNP]) {
+        if constexpr (kOct) Oct<T>::ld(tile + ri.at(wbi + 4 * q0 * es), f);
+        else Quad<T>::ld(tile + ri.at(wbi + 4 * q0 * es), *reinterpret_cast<float2(*)[2]>(&f[0]));
+    };
+    auto ld_dy = [&](const int q0, float2(&f)[kNP]) {
+        if constexpr (kOct && eo == 2) {
+            Oct<TO>::ld(to + ro.at(wbo + 4 * q0 * eo), f);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kNQ; ++j) Quad<TO>::ld(to + ro.at(wbo + 4 * (q0 + j) * eo), *reinterpret_cast<float2(*)[2]>(&f[2 * j]));
+        }
+    };
+    auto ld_bc = [&](const float *src, const int q0, float2(&f)[kNP]) {
+#pragma unroll
+        for (int j = 0; j < kNQ; ++j) Quad<float>::ld(reinterpret_cast<const char *>(src + 4 * (q0 + j)), *reinterpret_cast<float2(*)[2]>(&f[2 * j]));
+    };
     // ---- recompute a, a h_{t-1}, m of the block from the state entering it; dC_t = sum over rows of dy_t h_t on the way
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        if (kFull || (q >= qlo && q < qhi)) {
-            float2 dd[2], uu[2], Bv[2], dy[2];
-            Quad<T>::ld(td + ri.at(wbi + 4 * q * es), dd);
-            Quad<T>::ld(tu + ri.at(wbi + 4 * q * es), uu);
-            Quad<float>::ld(reinterpret_cast<const char *>(Bf + 4 * q), Bv);
-            Quad<TO>::ld(to + ro.at(wbo + 4 * q * eo), dy);
+    for (int sI = 0; sI < kNS; ++sI) {
+        const int q0 = sI * kNQ;
+        if (kFull || (q0 >= qlo && q0 < qhi)) {
+            float2 dd[kNP], uu[kNP], Bv[kNP], dy[kNP];
+            ld_in(td, q0, dd);
+            ld_in(tu, q0, uu);
+            ld_bc(Bf, q0, Bv);
+            ld_dy(q0, dy);
 #pragma unroll
-            for (int p = 0; p < 2; ++p) {
-                const int k = 2 * q + p;
+            for (int p = 0; p < kNP; ++p) {
+                const int k = 2 * q0 + p;
                 float2 m = fma2(dd[p], kL2E, bl2);                      // (delta + bias) log2e
                 if (kSoftplus) {
                     const float2 e = make_float2(ex2f(fminf(m.x, 120.f)), ex2f(fminf(m.y, 120.f)));
@@ -108,8 +133,14 @@ __device__ __forceinline__ void cw_bwd_block(const int qlo_in, const int qhi_in,
                 const float2 av = ex2_2(mul2(m, A2));
                 const float2 bv = mul2(mul2(m, uu[p]), Bv[p]);
                 float2 hp, hh;
-                hp.x = av.x * h; h = hp.x + bv.x; hh.x = h;             // a_t h_{t-1}, then h_t
+                // a_t h_{t-1}, then h_t
+#if MIA_CW_FMA
+                hp.x = __fmul_rn(av.x, h); h = fmaf(av.x, h, bv.x); hh.x = h;
+                hp.y = __fmul_rn(av.y, h); h = fmaf(av.y, h, bv.y); hh.y = h;
+#else
+                hp.x = av.x * h; h = hp.x + bv.x; hh.x = h;
                 hp.y = av.y * h; h = hp.y + bv.y; hh.y = h;
+#endif
                 R.a[k] = av; R.hp[k] = hp; R.m[k] = m;
                 const float2 dCv = mul2(dy[p], hh);
                 v[2 * k] = dCv.x; v[2 * k + 1] = dCv.y;
@@ -122,16 +153,17 @@ __device__ __forceinline__ void cw_bwd_block(const int qlo_in, const int qhi_in,
     for (int i = 0; i < 16; ++i) v[i] = 0.f;
     // ---- suffix recurrence G_t = a_t (dy_t C_t + G_{t+1}), gradients of the block
 #pragma unroll
-    for (int q = 3; q >= 0; --q) {
-        if (kFull || (q >= qlo && q < qhi)) {
-            float2 dy[2], Cv[2], Bv[2], uu[2], du[2], dd[2];
-            Quad<TO>::ld(to + ro.at(wbo + 4 * q * eo), dy);
-            Quad<float>::ld(reinterpret_cast<const char *>(Cf + 4 * q), Cv);
-            Quad<float>::ld(reinterpret_cast<const char *>(Bf + 4 * q), Bv);
-            Quad<T>::ld(tu + ri.at(wbi + 4 * q * es), uu);                    // u is still in the stage (du is written below)
+    for (int sI = kNS - 1; sI >= 0; --sI) {
+        const int q0 = sI * kNQ;
+        if (kFull || (q0 >= qlo && q0 < qhi)) {
+            float2 dy[kNP], Cv[kNP], Bv[kNP], uu[kNP], du[kNP], dd[kNP];
+            ld_dy(q0, dy);
+            ld_bc(Cf, q0, Cv);
+            ld_bc(Bf, q0, Bv);
+            ld_in(tu, q0, uu);                                          // u is still in the stage (du is written below)
 #pragma unroll
-            for (int p = 1; p >= 0; --p) {
-                const int k = 2 * q + p;
+            for (int p = kNP - 1; p >= 0; --p) {
+                const int k = 2 * q0 + p;
                 const float2 pc = mul2(dy[p], Cv[p]);
                 const float2 ap = mul2(R.a[k], pc);
                 float2 gg;
@@ -148,16 +180,24 @@ __device__ __forceinline__ void cw_bwd_block(const int qlo_in, const int qhi_in,
                 dA2 = fma2(gg, mul2(R.m[k], R.hp[k]), dA2);
                 dD2 = fma2(dy[p], uu[p], dD2);
             }
-            Quad<T>::st(tu + ri.at(wbi + 4 * q * es), du);                    // du replaces u, ddelta replaces delta
-            Quad<T>::st(td + ri.at(wbi + 4 * q * es), dd);
+            if constexpr (kOct) {
+                Oct<T>::st(tu + ri.at(wbi + 4 * q0 * es), du);          // du replaces u, ddelta replaces delta
+                Oct<T>::st(td + ri.at(wbi + 4 * q0 * es), dd);
+            } else {
+                Quad<T>::st(tu + ri.at(wbi + 4 * q0 * es), *reinterpret_cast<float2(*)[2]>(&du[0]));
+                Quad<T>::st(td + ri.at(wbi + 4 * q0 * es), *reinterpret_cast<float2(*)[2]>(&dd[0]));
+            }
         }
     }
     const float dBt = reduce16(v, lane, red);
     if (mine && lane < 16) accB[tok0 + i16] = dBt * kLn2;
 }
 
-template <typename T, bool kSoftplus, bool kOutF32, int kG>
-__global__ void __launch_bounds__(32, 12) ss_bwd_cw_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_d,
+// kMinBlk = resident one-warp CTAs per SM the register allocation is sized for: 12 -> 168 registers (three warps per scheduler);
+// 8 -> ptxas takes 247 and has no spills: same instructions, scheduled with the loads hoisted further.  The planner runs many
+// short items with 8 warps per SM anyway (plan_cw_bwd), so that build costs them no residency.
+template <typename T, bool kSoftplus, bool kOutF32, int kG, int kMinBlk>
+__global__ void __launch_bounds__(32, kMinBlk) ss_bwd_cw_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_d,
                                                            const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_du,
                                                            const __grid_constant__ CUtensorMap tm_dd, const __grid_constant__ CwBwdArgs a) {
     // The swizzled tiles need 1024-byte alignment.  The dynamic shared memory of a kernel without static shared memory starts at
@@ -375,15 +415,20 @@ __global__ void __launch_bounds__(32, 12) ss_bwd_cw_kernel(const __grid_constant
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-template <typename T, int kG>
-cudaError_t launch_bwd_cw_g(const CUtensorMap *tm, const CwBwdArgs &a, int grid, bool dout_f32, cudaStream_t stream) {
+template <typename T, int kG, int kMinBlk>
+cudaError_t launch_bwd_cw_gm(const CUtensorMap *tm, const CwBwdArgs &a, int grid, bool dout_f32, cudaStream_t stream) {
     void (*kernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CwBwdArgs);
-    if (a.softplus) kernel = dout_f32 ? &ss_bwd_cw_kernel<T, true, true, kG> : &ss_bwd_cw_kernel<T, true, false, kG>;
-    else kernel = dout_f32 ? &ss_bwd_cw_kernel<T, false, true, kG> : &ss_bwd_cw_kernel<T, false, false, kG>;
+    if (a.softplus) kernel = dout_f32 ? &ss_bwd_cw_kernel<T, true, true, kG, kMinBlk> : &ss_bwd_cw_kernel<T, true, false, kG, kMinBlk>;
+    else kernel = dout_f32 ? &ss_bwd_cw_kernel<T, false, true, kG, kMinBlk> : &ss_bwd_cw_kernel<T, false, false, kG, kMinBlk>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
     if (e != cudaSuccess) return e;
     kernel<<<grid, 32, a.smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], a);
     return cudaGetLastError();
+}
+
+template <typename T, int kG>
+cudaError_t launch_bwd_cw_g(const CUtensorMap *tm, const CwBwdArgs &a, int grid, bool dout_f32, cudaStream_t stream) {
+    return a.wide ? launch_bwd_cw_gm<T, kG, 8>(tm, a, grid, dout_f32, stream) : launch_bwd_cw_gm<T, kG, 12>(tm, a, grid, dout_f32, stream);
 }
 
 template <typename T>

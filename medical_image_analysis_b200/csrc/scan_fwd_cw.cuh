@@ -36,6 +36,9 @@
 namespace mia {
 
 constexpr int kCwTok = 32;       // columns per window
+#ifndef MIA_CW_OCT
+#define MIA_CW_OCT 1             // 0: the 8-byte (quad) tile accesses of the first version, kept for A/B timing (tools/ab_cw.py)
+#endif
 
 struct CwFwdArgs {
     int batch, dim, L, G, rows_per_group;
@@ -88,6 +91,7 @@ __global__ void __launch_bounds__(32, 16) ss_fwd_cw_kernel(const __grid_constant
     using raw = typename Cvt<T>::raw;
     constexpr int RBi = kCwTok * es, RBo = kCwTok * eo;
     constexpr int kTileI = 32 * RBi, kTileO = 32 * RBo;
+    constexpr bool kOct = es == 2 && MIA_CW_OCT;                         // 16-byte tile accesses (8 tokens) for 2-byte types
     const int lane = threadIdx.x;
     float *Bw = reinterpret_cast<float *>(smem + a.off_bc32), *Cw = Bw + kCwTok;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + a.off_bar);
@@ -194,15 +198,26 @@ __global__ void __launch_bounds__(32, 16) ss_fwd_cw_kernel(const __grid_constant
 
             // columns [ca, cb) of the window, all of one row
             auto run = [&](const int ca, const int cb) {
-                auto quad = [&](const int c) {
+                // kNQ quads = 4 kNQ tokens from column c on: one quad, or (2-byte types) two quads = one 16-byte access per tile
+                // and lane -- conflict-free on the swizzled tile where 8-byte accesses are not (Oct, scan_fwd_rows.cuh)
+                auto span = [&](const int c, auto nq_tag) {
+                    constexpr int kNQ = decltype(nq_tag)::value, kNP = 2 * kNQ;
                     const int lc = c - c0;
-                    float2 dd[2], uu[2], Bv[2], Cv[2], y[2];
-                    Quad<T>::ld(td + ri.at(lc * es), dd);
-                    Quad<T>::ld(tu + ri.at(lc * es), uu);
-                    Quad<float>::ld(reinterpret_cast<const char *>(Bw + lc), Bv);
-                    Quad<float>::ld(reinterpret_cast<const char *>(Cw + lc), Cv);
+                    float2 dd[kNP], uu[kNP], Bv[kNP], Cv[kNP], y[kNP];
+                    if constexpr (kNQ == 2) {
+                        Oct<T>::ld(td + ri.at(lc * es), dd);
+                        Oct<T>::ld(tu + ri.at(lc * es), uu);
+                    } else {
+                        Quad<T>::ld(td + ri.at(lc * es), dd);
+                        Quad<T>::ld(tu + ri.at(lc * es), uu);
+                    }
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {
+                    for (int j = 0; j < kNQ; ++j) {
+                        Quad<float>::ld(reinterpret_cast<const char *>(Bw + lc + 4 * j), *reinterpret_cast<float2(*)[2]>(&Bv[2 * j]));
+                        Quad<float>::ld(reinterpret_cast<const char *>(Cw + lc + 4 * j), *reinterpret_cast<float2(*)[2]>(&Cv[2 * j]));
+                    }
+#pragma unroll
+                    for (int q = 0; q < kNP; ++q) {
                         float2 m = fma2(dd[q], kL2E, bl2);              // (delta + bias) * log2e
                         if (kSoftplus) {
                             const float2 e = make_float2(ex2f(fminf(m.x, 120.f)), ex2f(fminf(m.y, 120.f)));
@@ -218,16 +233,37 @@ __global__ void __launch_bounds__(32, 16) ss_fwd_cw_kernel(const __grid_constant
                         h = fmaf(av.y, h, bv.y); hh.y = h;
                         y[q] = fma2(hh, Cv[q], mul2(uu[q], D2));
                     }
-                    if (kOutF32) Quad<float>::st(ty + ro.at(lc * 4), y);
-                    else Quad<T>::st(tu + ri.at(lc * es), y);           // y replaces u in place
-                    // state entering the next 16-column group (coalesced: 32 lanes x 4 bytes)
-                    if (hb && ((c + 4) & 15) == 0 && c + 4 < ncols) hb[((c + 4) >> 4) * 32] = h;
-                };
-                if (cb - ca == kCwTok) {
+                    if constexpr (kOutF32) {
 #pragma unroll
-                    for (int q = 0; q < kCwTok / 4; ++q) quad(ca + 4 * q);
+                        for (int j = 0; j < kNQ; ++j) Quad<float>::st(ty + ro.at((lc + 4 * j) * 4), *reinterpret_cast<float2(*)[2]>(&y[2 * j]));
+                    } else if constexpr (kNQ == 2) {
+                        Oct<T>::st(tu + ri.at(lc * es), y);             // y replaces u in place
+                    } else {
+                        Quad<T>::st(tu + ri.at(lc * es), y);
+                    }
+                    // state entering the next 16-column group (coalesced: 32 lanes x 4 bytes)
+                    const int ce = c + 4 * kNQ;
+                    if (hb && (ce & 15) == 0 && ce < ncols) hb[(ce >> 4) * 32] = h;
+                };
+                using One = std::integral_constant<int, 1>;
+                using Two = std::integral_constant<int, 2>;
+                if constexpr (kOct) {
+                    if (cb - ca == kCwTok) {
+#pragma unroll
+                        for (int q = 0; q < kCwTok / 8; ++q) span(ca + 8 * q, Two{});
+                    } else {                                             // (row ends are multiples of 4 columns, not of 8)
+                        int c = ca;
+                        if ((c & 4) && c < cb) { span(c, One{}); c += 4; }
+                        for (; c + 8 <= cb; c += 8) span(c, Two{});
+                        if (c < cb) span(c, One{});
+                    }
                 } else {
-                    for (int c = ca; c < cb; c += 4) quad(c);
+                    if (cb - ca == kCwTok) {
+#pragma unroll
+                        for (int q = 0; q < kCwTok / 4; ++q) span(ca + 4 * q, One{});
+                    } else {
+                        for (int c = ca; c < cb; c += 4) span(c, One{});
+                    }
                 }
             };
             // checkpoint (cumulative prod a, h) of the current row: at the chunk boundaries shared with the warp-scan kernels

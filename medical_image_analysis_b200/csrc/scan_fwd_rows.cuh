@@ -76,6 +76,47 @@ template <> struct Quad<float> {
     }
 };
 
+// 8 consecutive tokens of a 2-byte T (16 bytes, 16-byte aligned) <-> 4 float2.  Used on the swizzled TMA tiles of the
+// column-walk kernels: there the 32 lanes of a warp read the same column of 32 different tile rows, the swizzle permutes the
+// 16-byte chunks of 8 consecutive rows over one 128-byte bank line, and a 16-byte access per lane is conflict-free (each
+// quarter-warp covers the line exactly once), while 8-byte accesses hit every 8-byte bank pair twice per half-warp (ncu of the
+// quad version: a third of the shared-memory wavefronts of both kernels were bank conflicts, profiles/r2z_ncu_summary.json).
+template <typename T> struct Oct;
+template <> struct Oct<__nv_bfloat16> {
+    static __device__ __forceinline__ void ld(const char *p, float2 (&f)[4]) {
+        const uint4 w = *reinterpret_cast<const uint4 *>(p);
+        f[0] = make_float2(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u));
+        f[1] = make_float2(__uint_as_float(w.y << 16), __uint_as_float(w.y & 0xffff0000u));
+        f[2] = make_float2(__uint_as_float(w.z << 16), __uint_as_float(w.z & 0xffff0000u));
+        f[3] = make_float2(__uint_as_float(w.w << 16), __uint_as_float(w.w & 0xffff0000u));
+    }
+    static __device__ __forceinline__ void st(char *p, const float2 (&f)[4]) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0].x, f[0].y), h1 = __floats2bfloat162_rn(f[1].x, f[1].y),
+                       h2 = __floats2bfloat162_rn(f[2].x, f[2].y), h3 = __floats2bfloat162_rn(f[3].x, f[3].y);
+        *reinterpret_cast<uint4 *>(p) = make_uint4(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1),
+                                                   *reinterpret_cast<uint32_t *>(&h2), *reinterpret_cast<uint32_t *>(&h3));
+    }
+};
+template <> struct Oct<__half> {
+    static __device__ __forceinline__ void ld(const char *p, float2 (&f)[4]) {
+        uint4 w = *reinterpret_cast<const uint4 *>(p);
+        f[0] = __half22float2(*reinterpret_cast<__half2 *>(&w.x));
+        f[1] = __half22float2(*reinterpret_cast<__half2 *>(&w.y));
+        f[2] = __half22float2(*reinterpret_cast<__half2 *>(&w.z));
+        f[3] = __half22float2(*reinterpret_cast<__half2 *>(&w.w));
+    }
+    static __device__ __forceinline__ void st(char *p, const float2 (&f)[4]) {
+        __half2 h0 = __floats2half2_rn(f[0].x, f[0].y), h1 = __floats2half2_rn(f[1].x, f[1].y), h2 = __floats2half2_rn(f[2].x, f[2].y),
+                h3 = __floats2half2_rn(f[3].x, f[3].y);
+        *reinterpret_cast<uint4 *>(p) = make_uint4(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1),
+                                                   *reinterpret_cast<uint32_t *>(&h2), *reinterpret_cast<uint32_t *>(&h3));
+    }
+};
+template <> struct Oct<float> {                  // (two 16-byte accesses; fp32 tiles are conflict-free per quad already)
+    static __device__ __forceinline__ void ld(const char *, float2 (&)[4]) {}
+    static __device__ __forceinline__ void st(char *, const float2 (&)[4]) {}
+};
+
 template <typename T, bool kSoftplus, bool kOutF32>
 __global__ void __launch_bounds__(32) ss_fwd_rows_kernel(const __grid_constant__ RowsArgs a) {
     extern __shared__ __align__(128) char smem[];
