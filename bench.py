@@ -714,7 +714,7 @@ def main():
         except Exception as e:  # report, never hide
             line["modules"] = {"error": repr(e)}
 
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:               # (the CPU baseline is a rank-0, N = 1 figure)
         torch.set_num_threads(os.cpu_count() or 1)
         cv, cms, sample, cores = cpu_reference_run(ws[0], 2, 0, budget_s=20.0)
         line["cpu_baseline"] = {"value": cv, "unit": "patch-tokens/s", "cores": cores, "kind": "port", "sample": sample}
