@@ -49,6 +49,7 @@ struct CwFwdArgs {
     const void *A, *B, *C, *D, *delta_bias;
     float *x, *hblk;
     long long B_bs, B_gs, C_bs, C_gs;
+    int zero;                               // always 0 (the planner zero-fills the block); see `settle` in the kernel
 };
 
 // Per-lane view of its row inside a [32 rows][RB bytes] tile written by TMA (tile base 1024-byte aligned) with the swizzle whose
@@ -109,6 +110,13 @@ __global__ void __launch_bounds__(32, 16) ss_fwd_cw_kernel(const __grid_constant
     const float *biasp = reinterpret_cast<const float *>(a.delta_bias);
     const float2 kL2E = splat2(kLog2e), kOne = splat2(1.f);
     const SwzRow ri = swz_row<RBi>(lane), ro = swz_row<RBo>(lane);
+
+    // A / D loads are consumed where they are issued, by a value-preserving ALU op that ptxas cannot remove (a.zero is 0 at run
+    // time).  Otherwise their first use sits in the window loop and carries a wait on the scoreboard slot of these loads - the slot
+    // the loop's own B / C prefetch loads use too, so EVERY window waited for the prefetch it had just issued instead of one window
+    // later (ncu r2zz, profiles/README.md: 22 % of the warp samples of the L = 6400 forward on that one FMUL2, 11 % on one branch at
+    // L = 196; the wait masks: tools/sass_waits.py).
+    auto settle = [&](const float v) { return __uint_as_float(__float_as_uint(v) ^ (uint32_t)a.zero); };
 
     // first tensor-map row of an item, and its (batch, group) pair
     auto item_rows = [&](int item, int &b, int &gq, int &row0) {
@@ -171,8 +179,8 @@ __global__ void __launch_bounds__(32, 16) ss_fwd_cw_kernel(const __grid_constant
         const int srow0 = (b * a.dim + row0) / kG;
         int seg = 0;                                                     // row of the tensor-map row being walked
         int d = row0 + kG * lane;
-        float Araw = __ldg(Ap + d);
-        float2 bl2 = splat2((biasp ? __ldg(biasp + d) : 0.f) * kLog2e), A2 = splat2(Araw), D2 = splat2(Dp ? __ldg(Dp + d) : 0.f);
+        float Araw = settle(__ldg(Ap + d));
+        float2 bl2 = splat2((biasp ? __ldg(biasp + d) : 0.f) * kLog2e), A2 = splat2(Araw), D2 = splat2(settle(Dp ? __ldg(Dp + d) : 0.f));
         float h = 0.f;
         float2 msum = make_float2(0.f, 0.f);
         float2 *xrow = reinterpret_cast<float2 *>(a.x) + ((size_t)b * a.dim + d) * a.xchunks;
@@ -285,8 +293,8 @@ __global__ void __launch_bounds__(32, 16) ss_fwd_cw_kernel(const __grid_constant
                     checkpoint(e - seg * L);
                     if (e == row_end && seg + 1 < kG) {                  // next row: fresh state, its own A / D / bias
                         ++seg; d += 1;
-                        Araw = __ldg(Ap + d);
-                        bl2 = splat2((biasp ? __ldg(biasp + d) : 0.f) * kLog2e); A2 = splat2(Araw); D2 = splat2(Dp ? __ldg(Dp + d) : 0.f);
+                        Araw = settle(__ldg(Ap + d));
+                        bl2 = splat2((biasp ? __ldg(biasp + d) : 0.f) * kLog2e); A2 = splat2(Araw); D2 = splat2(settle(Dp ? __ldg(Dp + d) : 0.f));
                         h = 0.f; msum = make_float2(0.f, 0.f);
                         xrow += a.xchunks; xc = 0;
                     }
