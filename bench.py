@@ -642,7 +642,7 @@ def main():
         stress = {"every_step": {"value": sum(tokens) * world * args.steps / (s_ms * 1e-3), "ms_per_step": s_ms / args.steps,
                                  "bytes_per_step": ex_all.model_bytes, "bucket_mb": 100,
                                  "note": "whole gradient set all-reduced after EVERY scan step (not the headline: %dx a real step's traffic)"
-                                         % MODEL_SCAN_LAYERS}}
+                                         % exchange.report()["steps_per_gradient_set"]}}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
