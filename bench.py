@@ -699,6 +699,18 @@ def main():
                 v = ww["B"] * ww["L"] * 10 / (tms * 1e-3)
                 extras.append({"workload": name, "B": ww["B"], "value": v, "ms_per_step": tms / 10, "fwd_ms": f_ms[0], "bwd_ms": b_ms[0],
                                "bytes_per_token": fb + bb, "hbm_frac": v * (fb + bb) / 1e9 / peak})
+                if ww["N"] > 1:
+                    # d_state > 1 is bound by the MUFU (XU) pipe and instruction issue, not by HBM (SURVEY 8d asks for that share next
+                    # to the HBM share): the forward needs N exp2 for a = 2^(m A_n) + 2 for the softplus per row-token (+ 2 for
+                    # silu(z)), the SM retires 16 MUFU lanes per clock -> floor = row-tokens x MUFU / (16 x SMs x clock)
+                    mufu = ww["N"] + 2 + (2 if ww.get("z") else 0)
+                    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+                    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+                    floor_ms = ww["B"] * ww["R"] * ww["L"] * mufu / (16.0 * sms * mhz * 1e6) * 1e3
+                    extras[-1].update({"fwd_mufu_per_row_token": mufu, "fwd_mufu_floor_ms": floor_ms, "fwd_xu_pipe_frac": floor_ms / f_ms[0],
+                                       "bwd_xu_pipe_frac_ncu": 0.26 if name == "ss2d_m196_n16" else None,
+                                       "bwd_xu_source": "profiles/r2b_ncu_bwd_rowsn.json (sm__inst_executed_pipe_xu 26.1 %, issue-active 61.1 %)"
+                                       if name == "ss2d_m196_n16" else None})
                 del i2
                 torch.cuda.empty_cache()
             except Exception as e:  # report, never hide
